@@ -1,0 +1,243 @@
+"""ctypes binding of include/nbco.h (the C ABI).  No numerics here."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libnbco.so")
+
+EVAL_DIRECT3, EVAL_FMM3_KD, EVAL_COULOMB_DIRECT3, EVAL_COULOMB_FMM3_KD = 0, 1, 2, 3
+EULER, LEAPFROG, FORESTRUTH, PEFRL = 0, 1, 2, 3
+
+
+class NbcoError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    """nbco_config (include/nbco.h); replaces the globals of reference constants.cuh:36-52."""
+    _fields_ = [("device", C.c_int32), ("order", C.c_int32), ("radius", C.c_float), ("eps2", C.c_float),
+                ("dens_inhom", C.c_float), ("max_level", C.c_int32), ("tree_steps", C.c_int32),
+                ("coll", C.c_int32), ("unsort", C.c_int32), ("m2l_first", C.c_int32),
+                ("rank", C.c_int32), ("world", C.c_int32)]
+
+
+class FmmInfo(C.Structure):
+    _fields_ = [("levels", C.c_int32), ("order", C.c_int32), ("n", C.c_int64), ("nodes", C.c_int64),
+                ("p2p_pairs", C.c_int64), ("m2l_pairs", C.c_int64), ("off_m", C.c_int32), ("off_l", C.c_int32),
+                ("rebuilt", C.c_int32), ("mlt_max", C.c_int32), ("kernel_launches", C.c_int64)]
+
+
+# every symbol include/nbco.h declares (tests/test_abi.py checks this list against the header)
+SYMBOLS = [
+    "nbco_default_config", "nbco_abi_version", "nbco_last_error", "nbco_create", "nbco_destroy",
+    "nbco_set_config", "nbco_get_config", "nbco_stream", "nbco_force_direct3", "nbco_force_fmm3_kd",
+    "nbco_coulomb_direct3", "nbco_coulomb_fmm3_kd", "nbco_add_elastic", "nbco_step", "nbco_compute_force",
+    "nbco_integrate", "nbco_mean_rel_err", "nbco_energy", "nbco_eval_host", "nbco_run_host",
+    "nbco_fmm_get_info", "nbco_fmm_get_tree", "nbco_fmm_get_lists", "nbco_fmm_get_phase_ms",
+    "nbco_shard_range", "nbco_init_ga", "nbco_init_test_cube", "nbco_state_read", "nbco_state_write", "nbco_free",
+]
+
+
+def _load():
+    if not os.path.exists(lib_path):
+        raise NbcoError(f"{lib_path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no fallback implementation)")
+    L = C.CDLL(lib_path)
+    L.nbco_last_error.restype = C.c_char_p
+    L.nbco_stream.restype = C.c_void_p
+    L.nbco_stream.argtypes = [C.c_void_p]
+    L.nbco_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.nbco_destroy.argtypes = [C.c_void_p]
+    L.nbco_destroy.restype = None
+    L.nbco_set_config.argtypes = [C.c_void_p, C.POINTER(Config)]
+    L.nbco_get_config.argtypes = [C.c_void_p, C.POINTER(Config)]
+    vp, i64, f32, f64 = C.c_void_p, C.c_int64, C.c_float, C.c_double
+    L.nbco_force_direct3.argtypes = [vp, vp, vp, i64, vp]
+    L.nbco_force_fmm3_kd.argtypes = [vp, vp, vp, i64, vp]
+    L.nbco_coulomb_direct3.argtypes = [vp, vp, vp, i64, vp]
+    L.nbco_coulomb_fmm3_kd.argtypes = [vp, vp, vp, i64, vp]
+    L.nbco_add_elastic.argtypes = [vp, vp, vp, i64, vp]
+    L.nbco_step.argtypes = [vp, vp, vp, f32, i64]
+    L.nbco_compute_force.argtypes = [vp, C.c_int, vp, i64, vp]
+    L.nbco_integrate.argtypes = [vp, C.c_int, C.c_int, vp, i64, vp, f64, i64]
+    L.nbco_mean_rel_err.argtypes = [vp, vp, vp, i64, C.POINTER(f64), C.POINTER(f64)]
+    L.nbco_energy.argtypes = [vp, vp, i64, vp, C.POINTER(f64)]
+    L.nbco_eval_host.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp]
+    L.nbco_run_host.argtypes = [vp, C.c_int, C.c_int, vp, vp, i64, vp, f64, i64]
+    L.nbco_fmm_get_info.argtypes = [vp, C.POINTER(FmmInfo)]
+    L.nbco_fmm_get_tree.argtypes = [vp] + [vp] * 9
+    L.nbco_fmm_get_lists.argtypes = [vp, vp, i64, vp, i64]
+    L.nbco_fmm_get_phase_ms.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(f32), C.c_int]
+    L.nbco_shard_range.argtypes = [i64, C.c_int32, C.c_int32, C.POINTER(i64), C.POINTER(i64)]
+    L.nbco_shard_range.restype = None
+    L.nbco_init_ga.argtypes = [vp, i64, vp, vp]
+    L.nbco_init_test_cube.argtypes = [vp, i64, vp, vp]
+    L.nbco_state_read.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(i64)]
+    L.nbco_state_write.argtypes = [C.c_char_p, vp, i64]
+    L.nbco_free.argtypes = [vp]
+    L.nbco_free.restype = None
+    return L
+
+
+lib = _load()
+
+
+def _check(status):
+    if status != 0:
+        raise NbcoError(f"nbco status {status}: {lib.nbco_last_error().decode()}")
+
+
+def _hp(a):
+    """host pointer of a C-contiguous numpy array (or None)"""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_config(**kw):
+    cfg = Config()
+    lib.nbco_default_config(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise KeyError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def default_param(n, xi=2e-6, omega0=(1.095, 1.0, 1.0)):
+    """parameter block of main3.cu:685-692: {xi/N, 0, 0, w0x^2, w0y^2, w0z^2}"""
+    w = np.asarray(omega0, np.float32)
+    return np.array([np.float32(xi) / np.float32(n), 0, 0, w[0] * w[0], w[1] * w[1], w[2] * w[2]], np.float32)
+
+
+def init_ga(n, sigma_x=(0.003, 0.001, 0.01), omega0=(1.095, 1.0, 1.0)):
+    """reference initGA state [pos|vel] as a (2, n, 3) float32 array (main3.cu:241-245,662-664)"""
+    sx = np.asarray(sigma_x, np.float32)
+    su = (np.asarray(omega0, np.float32) * sx).astype(np.float32)
+    out = np.empty((2, n, 3), np.float32)
+    _check(lib.nbco_init_ga(_hp(out), n, _hp(sx), _hp(su)))
+    return out
+
+
+def init_test_cube(n, sigma_x=(0.003, 0.001, 0.01), omega0=(1.095, 1.0, 1.0)):
+    sx = np.asarray(sigma_x, np.float32)
+    su = (np.asarray(omega0, np.float32) * sx).astype(np.float32)
+    out = np.empty((2, n, 3), np.float32)
+    _check(lib.nbco_init_test_cube(_hp(out), n, _hp(sx), _hp(su)))
+    return out
+
+
+def shard_range(n, rank, world):
+    b, e = C.c_int64(), C.c_int64()
+    lib.nbco_shard_range(n, rank, world, C.byref(b), C.byref(e))
+    return b.value, e.value
+
+
+class Context:
+    """Owns one nbco_ctx.  Device-pointer methods take integers (e.g. torch_tensor.data_ptr())."""
+
+    def __init__(self, **cfg):
+        self.cfg = default_config(**cfg)
+        self._h = C.c_void_p()
+        _check(lib.nbco_create(C.byref(self.cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.nbco_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.cfg, k):
+                raise KeyError(k)
+            setattr(self.cfg, k, v)
+        _check(lib.nbco_set_config(self._h, C.byref(self.cfg)))
+
+    @property
+    def stream(self):
+        return lib.nbco_stream(self._h)
+
+    # ---- device-pointer calls (the reference plugin signature) ----
+    def force_direct3(self, d_pos, d_acc, n, d_param=None):
+        _check(lib.nbco_force_direct3(self._h, d_pos, d_acc, n, d_param))
+
+    def force_fmm3_kd(self, d_pos, d_acc, n, d_param=None):
+        _check(lib.nbco_force_fmm3_kd(self._h, d_pos, d_acc, n, d_param))
+
+    def coulomb_direct3(self, d_pos, d_acc, n, d_param=None):
+        _check(lib.nbco_coulomb_direct3(self._h, d_pos, d_acc, n, d_param))
+
+    def coulomb_fmm3_kd(self, d_pos, d_acc, n, d_param=None):
+        _check(lib.nbco_coulomb_fmm3_kd(self._h, d_pos, d_acc, n, d_param))
+
+    def add_elastic(self, d_pos, d_acc, n, d_k3=None):
+        _check(lib.nbco_add_elastic(self._h, d_pos, d_acc, n, d_k3))
+
+    def step(self, d_b, d_a, ds, n):
+        _check(lib.nbco_step(self._h, d_b, d_a, ds, n))
+
+    def compute_force(self, evaluator, d_buf, n, d_param=None):
+        _check(lib.nbco_compute_force(self._h, evaluator, d_buf, n, d_param))
+
+    def integrate(self, scheme, evaluator, d_buf, n, d_param, dt, nsteps):
+        _check(lib.nbco_integrate(self._h, scheme, evaluator, d_buf, n, d_param, dt, nsteps))
+
+    def mean_rel_err(self, d_a, d_ref, n):
+        m, x = C.c_double(), C.c_double()
+        _check(lib.nbco_mean_rel_err(self._h, d_a, d_ref, n, C.byref(m), C.byref(x)))
+        return m.value, x.value
+
+    def energy(self, d_buf, n, d_param=None):
+        out = (C.c_double * 3)()
+        _check(lib.nbco_energy(self._h, d_buf, n, d_param, out))
+        return tuple(out)
+
+    # ---- host-buffer calls ----
+    def eval_host(self, evaluator, pos, vel=None, param=None):
+        """pos (n,3) float32 [updated in place when the FMM leaves tree order]; returns acc (n,3)"""
+        n = pos.shape[0]
+        acc = np.empty((n, 3), np.float32)
+        _check(lib.nbco_eval_host(self._h, evaluator, _hp(pos), _hp(vel), _hp(acc), n, _hp(param)))
+        return acc
+
+    def run_host(self, scheme, evaluator, pos_vel, param, dt, nsteps, want_acc=False):
+        """pos_vel (2,n,3) float32, updated in place"""
+        n = pos_vel.shape[1]
+        acc = np.empty((n, 3), np.float32) if want_acc else None
+        _check(lib.nbco_run_host(self._h, scheme, evaluator, _hp(pos_vel), _hp(acc), n, _hp(param), dt, nsteps))
+        return acc
+
+    # ---- FMM introspection ----
+    def fmm_info(self):
+        info = FmmInfo()
+        _check(lib.nbco_fmm_get_info(self._h, C.byref(info)))
+        return info
+
+    def fmm_tree(self):
+        i = self.fmm_info()
+        nn, n = i.nodes, i.n
+        t = dict(center=np.empty((nn, 3), np.float32), lbound=np.empty((nn, 3), np.float32),
+                 rbound=np.empty((nn, 3), np.float32), mpole=np.empty((nn, i.off_m), np.float32),
+                 local=np.empty((nn, i.off_l), np.float32), mult=np.empty(nn, np.int32),
+                 index=np.empty(nn, np.int32), splitdim=np.empty(nn, np.int32), perm=np.empty(n, np.int32))
+        _check(lib.nbco_fmm_get_tree(self._h, _hp(t["center"]), _hp(t["lbound"]), _hp(t["rbound"]), _hp(t["mpole"]),
+                                     _hp(t["local"]), _hp(t["mult"]), _hp(t["index"]), _hp(t["splitdim"]), _hp(t["perm"])))
+        t["levels"] = i.levels
+        return t
+
+    def fmm_lists(self):
+        i = self.fmm_info()
+        p2p = np.empty((i.p2p_pairs, 2), np.int32)
+        m2l = np.empty((i.m2l_pairs, 2), np.int32)
+        _check(lib.nbco_fmm_get_lists(self._h, _hp(p2p), i.p2p_pairs, _hp(m2l), i.m2l_pairs))
+        return p2p, m2l
+
+    def fmm_phase_ms(self):
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        k = lib.nbco_fmm_get_phase_ms(self._h, names, ms, 32)
+        return {names[j].decode(): ms[j] for j in range(k)}

@@ -1,0 +1,90 @@
+// common.cuh -- shared declarations of the sm_100a implementation behind include/nbco.h
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nbco.h"
+
+namespace nbco {
+
+constexpr int kSMs = 148; // B200: 2 dies x 74 SMs; the real count is queried at context creation
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define NBCO_CUDA(expr)                                                              \
+	do {                                                                             \
+		cudaError_t e__ = (expr);                                                    \
+		if (e__ != cudaSuccess) return ::nbco::cuda_fail(e__, #expr, __FILE__, __LINE__); \
+	} while (0)
+
+#define NBCO_TRY(expr)                      \
+	do {                                    \
+		int s__ = (expr);                   \
+		if (s__ != NBCO_OK) return s__;     \
+	} while (0)
+
+// Growable device buffer owned by a context (replaces the function-local statics of
+// fmm_cart3_kdtree.cuh:1480-1498; never shrinks, freed with the context).
+struct DevBuf
+{
+	void *p = nullptr;
+	size_t bytes = 0;
+	int reserve(size_t need);
+	void release();
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct FmmPlan; // fmm3.cu
+
+} // namespace nbco
+
+struct nbco_ctx
+{
+	nbco_config cfg;
+	int sm_count = nbco::kSMs;
+	cudaStream_t stream = nullptr;
+	int64_t launches = 0; // kernels launched through this context
+
+	// direct sum scratch
+	nbco::DevBuf pos4;      // float4-padded copy of the sources
+	// diagnostics scratch
+	nbco::DevBuf red;       // reduction partials
+	// host-call staging
+	nbco::DevBuf h_state;   // [pos|vel|acc] for nbco_eval_host / nbco_run_host
+	nbco::DevBuf h_param;
+	void *pinned = nullptr; size_t pinned_bytes = 0;
+
+	nbco::FmmPlan *fmm = nullptr;
+};
+
+namespace nbco {
+
+// direct.cu
+int direct3_launch(nbco_ctx *ctx, const float *d_pos, float *d_acc, int64_t n, const float *d_param);
+int pair_energy_launch(nbco_ctx *ctx, const float *d_pos, int64_t n, double *d_out);
+// integrate.cu
+int add_elastic_launch(nbco_ctx *ctx, const float *d_pos, float *d_acc, int64_t n, const float *d_k3);
+int step_launch(nbco_ctx *ctx, float *d_b, const float *d_a, float ds, int64_t n);
+int rel_err_launch(nbco_ctx *ctx, const float *d_a, const float *d_ref, int64_t n, double *h_mean, double *h_max);
+int kinetic_elastic_launch(nbco_ctx *ctx, const float *d_buf, int64_t n, const float *d_param, double *h_out2);
+// fmm3.cu
+int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const float *d_param, bool fuse_elastic);
+void fmm3_destroy(nbco_ctx *ctx);
+
+inline int grid_for(int64_t work, int block, int sm_count, int per_sm)
+{
+	int64_t g = (work + block - 1) / block;
+	int64_t cap = (int64_t)sm_count * per_sm;
+	if (g > cap) g = cap;
+	if (g < 1) g = 1;
+	return (int)g;
+}
+
+} // namespace nbco

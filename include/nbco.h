@@ -1,0 +1,180 @@
+/* nbco.h -- C ABI of the B200-native force-evaluation / time-stepping path.
+ *
+ * Drop-in boundary for locuoco/coulomb_oscillators (reference paths are relative to its
+ * Simulation/ directory).  Every entry point replaces one reference interface and is what a
+ * maintainer would bind in place of it (see INTEGRATION.md for the reference-side stub):
+ *
+ *   reference plugin type   void f(VEC *p, VEC *a, int n, const SCAL *param)   integrator.cuh:22
+ *   reference step type     void step(VEC *b, const VEC *a, SCAL ds, int n)    integrator.cuh:34, kernel.cuh:100
+ *
+ * Conventions kept from the reference:
+ *   - VEC = float3 stored AoS (12 B, x y z), SCAL = float (constants.cuh:22-28);
+ *   - the state buffer is one allocation [pos(n) | vel(n) | acc(n)] (integrator.cuh:24);
+ *   - param is a DEVICE array {xi/N, 0, 0, kx, ky, kz} (main3.cu:685-692); the Coulomb evaluators
+ *     read param[0], the elastic term reads param+3; param == NULL means "unscaled"
+ *     (fmm_cart3_kdtree.cuh:1743, kernel.cuh:148-151);
+ *   - with unsort == 0 the FMM evaluator permutes pos AND the velocities stored at pos+n in
+ *     place into tree order on tree-rebuild calls (fmm_cart3_kdtree.cuh:1359-1360,1758-1759);
+ *   - evaluators return after the work has completed on the device (:1762-1763).
+ * Differences, all deliberate: configuration is an explicit struct instead of the mutable
+ * globals of constants.cuh:36-52; scratch memory belongs to a context instead of function
+ * statics; errors are returned (never exit()); sizes are 64-bit.
+ *
+ * No torch types, no C++ types: plain pointers and sizes only.  Pointers named d_* are device
+ * pointers on the context's device, h_* are host pointers.  There is no CPU fallback: every
+ * call needs a CUDA device and fails with NBCO_ERR_CUDA otherwise.
+ */
+#ifndef NBCO_H
+#define NBCO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBCO_ABI_VERSION 1
+
+typedef struct nbco_ctx nbco_ctx;
+
+enum nbco_status
+{
+	NBCO_OK = 0,
+	NBCO_ERR_INVALID = 1,   /* bad argument / unsupported configuration */
+	NBCO_ERR_CUDA = 2,      /* CUDA runtime error, text in nbco_last_error() */
+	NBCO_ERR_NOMEM = 3,
+	NBCO_ERR_OVERFLOW = 4   /* an interaction list did not fit (never silently truncated) */
+};
+
+/* Replaces the globals of constants.cuh:36-52 (+ CLI options of main3.cu:263-305). */
+typedef struct nbco_config
+{
+	int32_t device;        /* CUDA device ordinal (reference: hard-wired 0, fmm_cart3_kdtree.cuh:1529) */
+	int32_t order;         /* fmm_order, "-p"; default 3 (constants.cuh:42); 1..NBCO_MAX_ORDER */
+	float   radius;        /* tree_radius, "-r"; default 1 */
+	float   eps2;          /* EPS2 = eps^2, "-eps"; default 1e-18; must be > 0 */
+	float   dens_inhom;    /* dens_inhom, "-i"; default 1 */
+	int32_t max_level;     /* tree_L, "-maxlevel"; 0 = automatic (fmm_cart3_kdtree.cuh:1508-1516) */
+	int32_t tree_steps;    /* tree_steps: rebuild the kd-tree every this many evaluations; default 8 */
+	int32_t coll;          /* 0 = "-ncoll": skip the P2P near field */
+	int32_t unsort;        /* b_unsort: 1 = return pos/acc in input order, 0 = leave tree order */
+	int32_t m2l_first;     /* 1 = MAC before leaf test (reference GPU kernel, :504-534),
+	                          0 = leaf test first (reference CPU path, :586-598) */
+	int32_t rank;          /* multi-GPU: this process' rank and the world size; the evaluators then */
+	int32_t world;         /* compute only this rank's shard of targets (see nbco_shard_range)      */
+} nbco_config;
+
+#define NBCO_MAX_ORDER 8
+
+void nbco_default_config(nbco_config *cfg);
+int  nbco_abi_version(void);
+const char *nbco_last_error(void);
+
+int  nbco_create(const nbco_config *cfg, nbco_ctx **out);
+void nbco_destroy(nbco_ctx *ctx);
+int  nbco_set_config(nbco_ctx *ctx, const nbco_config *cfg);    /* re-plans lazily, like :1502 */
+int  nbco_get_config(const nbco_ctx *ctx, nbco_config *cfg);
+/* The CUDA stream every call of this context is enqueued on (a cudaStream_t), for callers
+ * that want to bracket calls with their own events. */
+void *nbco_stream(nbco_ctx *ctx);
+
+/* ---- evaluators: the reference plugin type, device pointers ---- */
+
+/* direct3 (direct.cuh:233-245): a_i = param[0] * sum_j d (|d|^2+eps2)^(-3/2), d = x_i - x_j.
+ * Multi-GPU: d_pos holds all n sources; only targets of this rank's shard are written. */
+int nbco_force_direct3(nbco_ctx *ctx, const void *d_pos, void *d_acc, int64_t n, const void *d_param);
+
+/* fmm_cart3_kdtree (fmm_cart3_kdtree.cuh:1478-1771). d_pos is followed by the velocities at
+ * d_pos + n (float3) when unsort == 0, exactly like the reference. */
+int nbco_force_fmm3_kd(nbco_ctx *ctx, void *d_pos, void *d_acc, int64_t n, const void *d_param);
+
+/* coulombOscillatorDirect / coulombOscillatorFMMKD3 (main3.cu:47-63): evaluator + elastic term */
+int nbco_coulomb_direct3(nbco_ctx *ctx, void *d_pos, void *d_acc, int64_t n, const void *d_param);
+int nbco_coulomb_fmm3_kd(nbco_ctx *ctx, void *d_pos, void *d_acc, int64_t n, const void *d_param);
+
+/* add_elastic (kernel.cuh:145-152): a -= k o x, d_k3 = device float[3] or NULL (k = 1) */
+int nbco_add_elastic(nbco_ctx *ctx, const void *d_pos, void *d_acc, int64_t n, const void *d_k3);
+
+/* step (kernel.cuh:100-104): b += a * ds */
+int nbco_step(nbco_ctx *ctx, void *d_b, const void *d_a, float ds, int64_t n);
+
+/* ---- integrators (integrator.cuh:32-167) over the state buffer [pos|vel|acc] ---- */
+enum nbco_scheme  { NBCO_EULER = 0, NBCO_LEAPFROG = 1, NBCO_FORESTRUTH = 2, NBCO_PEFRL = 3 };
+enum nbco_evaluator { NBCO_EVAL_DIRECT3 = 0, NBCO_EVAL_FMM3_KD = 1,
+                      NBCO_EVAL_COULOMB_DIRECT3 = 2, NBCO_EVAL_COULOMB_FMM3_KD = 3 };
+
+/* compute_force (integrator.cuh:22-28) */
+int nbco_compute_force(nbco_ctx *ctx, int evaluator, void *d_buf, int64_t n, const void *d_param);
+/* nsteps steps of the chosen scheme; the caller does the initial compute_force like
+ * main3.cu:835-839.  dt is rounded to float first (main3.cu:231). */
+int nbco_integrate(nbco_ctx *ctx, int scheme, int evaluator, void *d_buf, int64_t n,
+                   const void *d_param, double dt, int64_t nsteps);
+
+/* ---- diagnostics ---- */
+/* mean over i of |a-ref| / sqrt(|ref|^2 + 1e-18) (rel_diff1, reductions.cuh:37-42; the index
+ * bug of relerrReduce2 :89 is not reproduced).  Result on the host. */
+int nbco_mean_rel_err(nbco_ctx *ctx, const void *d_a, const void *d_ref, int64_t n, double *h_mean, double *h_max);
+/* Energy of the Coulomb-oscillator system (absent in the reference):
+ * h_out[0] = sum 1/2 v^2, h_out[1] = 1/2 sum k o x^2, h_out[2] = param[0] * sum_{i<j} (d^2+eps2)^(-1/2)
+ * (pair term by direct summation, O(n^2)). */
+int nbco_energy(nbco_ctx *ctx, const void *d_buf, int64_t n, const void *d_param, double *h_out3);
+
+/* ---- host-buffer convenience (the e2e path: H2D + evaluate + D2H in one call) ---- */
+/* h_param = host float[6] or NULL.  evaluator as above.  h_pos (and h_vel when given and
+ * unsort == 0) are updated like the device call would update them. */
+int nbco_eval_host(nbco_ctx *ctx, int evaluator, float *h_pos, float *h_vel, float *h_acc,
+                   int64_t n, const float *h_param);
+/* Whole run from host state [pos|vel] (the binary state-file layout, main3.cu:629-652):
+ * H2D, compute_force, nsteps steps, D2H of pos|vel (acc too when h_acc != NULL). */
+int nbco_run_host(nbco_ctx *ctx, int scheme, int evaluator, float *h_pos_vel, float *h_acc, int64_t n,
+                  const float *h_param, double dt, int64_t nsteps);
+
+/* ---- introspection of the last FMM evaluation (parity tests, profiling) ---- */
+typedef struct nbco_fmm_info
+{
+	int32_t levels;        /* L: leaves are level L, root level 0 */
+	int32_t order;
+	int64_t n;
+	int64_t nodes;         /* 2^(L+1)-1 */
+	int64_t p2p_pairs, m2l_pairs;
+	int32_t off_m, off_l;  /* floats per node: symmetric orders 0..p-1, traceless orders 0..p */
+	int32_t rebuilt;       /* 1 if the last evaluation rebuilt the tree */
+	int32_t mlt_max;
+	int64_t kernel_launches; /* kernels launched by this context so far */
+} nbco_fmm_info;
+
+int nbco_fmm_get_info(nbco_ctx *ctx, nbco_fmm_info *info);
+/* Copies to host whatever pointers are non-NULL.  Layouts follow fmmTree_kd
+ * (fmm_cart3_kdtree.cuh:25-31, slab :1552-1560): center/lbound/rbound float3 per node;
+ * mpole off_m floats per node (symmetric storage, fmm_cart_base3.cuh:180-213); local off_l
+ * floats per node (traceless storage, :185-232); mult/index/splitdim int per node (index has
+ * one extra entry per level as in evalBox, not exported: index[node] only).
+ * perm[n]: sorted position -> position in the array passed to the last rebuild (d_unsort).
+ * Lists are int2 pairs sorted ascending by (x, y) so that they can be compared as sets. */
+int nbco_fmm_get_tree(nbco_ctx *ctx, float *h_center, float *h_lbound, float *h_rbound,
+                      float *h_mpole, float *h_local, int32_t *h_mult, int32_t *h_index,
+                      int32_t *h_splitdim, int32_t *h_perm);
+int nbco_fmm_get_lists(nbco_ctx *ctx, int32_t *h_p2p_pairs, int64_t p2p_cap,
+                       int32_t *h_m2l_pairs, int64_t m2l_cap);
+/* Per-phase device times (ms) of the last FMM evaluation, measured with CUDA events on the
+ * context stream: names[i] points to a static string. Returns the number of phases. */
+int nbco_fmm_get_phase_ms(nbco_ctx *ctx, const char **names, float *ms, int cap);
+
+/* ---- multi-GPU helpers ---- */
+/* Target shard [begin, end) of rank r of w over n items: the kd-tree's own equal split
+ * ceil(n*r/w) (fmm_cart3_kdtree.cuh:117-118). */
+void nbco_shard_range(int64_t n, int32_t rank, int32_t world, int64_t *begin, int64_t *end);
+
+/* ---- initial conditions and state files (host side, byte-compatible with main3.cu) ---- */
+/* initGA with the reference's fixed seed (main3.cu:114-137,662-664): h_pos_vel = 6n floats */
+int nbco_init_ga(float *h_pos_vel, int64_t n, const float *sigma_x3, const float *sigma_u3);
+/* the "-test" uniform cube [-1,1]^3 drawn after initGA from the same generator (main3.cu:94-112,665-666) */
+int nbco_init_test_cube(float *h_pos_vel, int64_t n, const float *sigma_x3, const float *sigma_u3);
+int nbco_state_read(const char *path, float **h_pos_vel, int64_t *n);   /* caller frees with nbco_free */
+int nbco_state_write(const char *path, const float *h_pos_vel, int64_t n);
+void nbco_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBCO_H */
