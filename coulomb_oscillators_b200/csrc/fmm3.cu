@@ -1,13 +1,970 @@
-// fmm3.cu -- placeholder while the kd-tree FMM kernels are being brought up.
-#include "common.cuh"
+// fmm3.cu -- 3D Cartesian FMM on a balanced kd-tree for sm_100a.
+//
+// Replaces fmm_cart3_kdtree (reference Simulation/fmm_cart3_kdtree.cuh:1478-1771) and everything it
+// launches: CUB radix sort + bb_segsort + gather/copy passes per level (:1311-1364), evalBox/evalKeys
+// (:109-202), centerLeaves/multLeaves (appel.cuh:184-258), P2M/M2M (:231-393), the 18-block dual
+// traversal (:416-567), P2P (:767-1132), M2L (:613-765), L2L/L2P (:1134-1309), rescale
+// (appel.cuh:506-527) and, for the coulombOscillator evaluator, add_elastic (kernel.cuh:119-152).
+//
+// Design (DESIGN.md has the long form):
+//  * the tree is the reference's: node i of level l owns sorted range [ceil(n i/2^l), ceil(n (i+1)/2^l)),
+//    split axis = widest box extent, child boxes cut at the boundary particles' coordinates.  index/mult
+//    are pure functions of (n, l, i) and are never stored.
+//  * build: only (fp32 key, u32 id) pairs are sorted.  Levels whose segments exceed kBottomCap
+//    particles run one stable segmented LSD radix sort each (4 x 8 bit, per-segment digit offsets,
+//    warp-match ranking); all remaining levels run in ONE kernel, a CTA per subtree holding its
+//    particles in shared memory (bitonic sort of 64-bit (key,slot) words in power-of-two blocks).
+//    Equal keys are ordered as a stable sort at every level would order them (ties fall back to
+//    the coordinates of the previous split axes, then the input index).  One gather at the end.
+//  * geometry that decides the interaction lists (centres, box sizes, MAC) is evaluated with the
+//    reference's host operation order and no FMA contraction (__fmul_rn/__fadd_rn), the MAC's
+//    pow() is a host-computed table (only two multiplicities exist per level), so tree arrays and
+//    lists are bit-exact against the reference's CPU path.
+//  * traversal is level-synchronous over all SMs (the reference uses 18 blocks), frontier in global
+//    memory, warp-aggregated appends.
+//  * operators are compile-time unrolled templates (fmm_ops.cuh), one instantiation per order.
+
+#include "fmm3_common.cuh"
+
 namespace nbco {
-int fmm3_kd_launch(nbco_ctx *, float *, float *, int64_t, const float *, bool)
-{ set_error("fmm3_kd: not built yet"); return NBCO_ERR_INVALID; }
-void fmm3_destroy(nbco_ctx *) {}
+
+namespace {
+
+// =====================================================================================
+//  bounding box (replaces minmaxReduce2, reductions.cuh:67-80: two CUB passes -> one pass)
+// =====================================================================================
+__global__ void __launch_bounds__(256) bbox_kernel(const float *__restrict__ pos, int64_t n, u32 *__restrict__ out6)
+{
+	float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+	{
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			float v = pos[3*i+k];
+			mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v);
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < 3; ++k)
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+			mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+		}
+	if ((threadIdx.x & 31) == 0)
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			atomicMin(out6 + k, ordered_bits(mn[k]));
+			atomicMax(out6 + 3 + k, ordered_bits(mx[k]));
+		}
 }
+
+__global__ void root_box_kernel(TreeGeom g, const u32 *__restrict__ bb)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0)
+	{
+		float lb[3], rb[3];
+		for (int k = 0; k < 3; ++k) { lb[k] = unordered_bits(bb[k]); rb[k] = unordered_bits(bb[3+k]); }
+		write_box(g, 0, lb, rb, kNoAxis | (kNoAxis << 2) | (kNoAxis << 4));
+	}
+}
+
+// =====================================================================================
+//  top levels: segmented stable LSD radix sort of (key, id) pairs
+// =====================================================================================
+
+// boxes of level l from the sorted keys of level l-1 (evalBox_krnl, :109-137)
+__global__ void __launch_bounds__(256) evalbox_top_kernel(TreeGeom g, const u32 *__restrict__ keys, int64_t n, int l)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= (1 << l)) return;
+	int node = kd_beg(l) + j, parent = (node - 1) >> 1, split = g.splitdim[parent];
+	float lb[3], rb[3];
+	for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*parent+k]; rb[k] = g.rbound[3*parent+k]; }
+	int64_t s0 = seg_start(n, j, l), s1 = seg_start(n, j + 1, l);
+	if (node == 2*parent + 2) lb[split] = unordered_bits(keys[s0]);
+	else rb[split] = unordered_bits(keys[s1 - 1]);
+	write_box(g, node, lb, rb, g.chain[parent]);
+}
+
+struct TileRange { int64_t a, b; int seg; };
+
+__device__ __forceinline__ TileRange tile_range(int64_t n, int l, int tps)
+{
+	TileRange r;
+	r.seg = blockIdx.x / tps;
+	int t = blockIdx.x % tps;
+	int64_t s0 = seg_start(n, r.seg, l), s1 = seg_start(n, r.seg + 1, l);
+	r.a = s0 + (int64_t)t * kTile;
+	r.b = r.a + kTile < s1 ? r.a + kTile : s1;
+	return r;
+}
+
+// keys of level l (evalKeys_kdtree, :158-192) fused with the digit-0 histogram
+__global__ void __launch_bounds__(256)
+keygen_hist_kernel(const float *__restrict__ pos, const int *__restrict__ splitdim, const u32 *__restrict__ idx_in,
+                   u32 *__restrict__ keys, u32 *__restrict__ idx_out, u32 *__restrict__ hist, int64_t n, int l, int tps)
+{
+	__shared__ u32 sh[256];
+	sh[threadIdx.x] = 0;
+	__syncthreads();
+	TileRange r = tile_range(n, l, tps);
+	const int axis = splitdim[kd_beg(l) + r.seg];
+	for (int64_t j = r.a + threadIdx.x; j < r.b; j += 256)
+	{
+		u32 id = idx_in ? idx_in[j] : (u32)j;
+		u32 key = ordered_bits(pos[3 * (int64_t)id + axis]);
+		keys[j] = key;
+		if (!idx_in) idx_out[j] = id;
+		atomicAdd(&sh[key & 255u], 1u);
+	}
+	__syncthreads();
+	hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256)
+hist_kernel(const u32 *__restrict__ keys, u32 *__restrict__ hist, int64_t n, int l, int tps, int shift)
+{
+	__shared__ u32 sh[256];
+	sh[threadIdx.x] = 0;
+	__syncthreads();
+	TileRange r = tile_range(n, l, tps);
+	for (int64_t j = r.a + threadIdx.x; j < r.b; j += 256)
+		atomicAdd(&sh[(keys[j] >> shift) & 255u], 1u);
+	__syncthreads();
+	hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
+}
+
+// per segment: counts -> destination offsets, ordered (digit, tile); in place
+__global__ void __launch_bounds__(256) seg_scan_kernel(u32 *__restrict__ hist, int64_t n, int l, int tps)
+{
+	__shared__ u32 sh[256];
+	const int seg = blockIdx.x, d = threadIdx.x;
+	u32 *h = hist + (int64_t)seg * tps * 256;
+	u32 total = 0;
+	for (int t = 0; t < tps; ++t) total += h[t * 256 + d];
+	sh[d] = total;
+	__syncthreads();
+	for (int o = 1; o < 256; o <<= 1) // inclusive Hillis-Steele scan over the 256 digits
+	{
+		u32 v = (d >= o) ? sh[d - o] : 0;
+		__syncthreads();
+		sh[d] += v;
+		__syncthreads();
+	}
+	u32 run = (u32)seg_start(n, seg, l) + sh[d] - total;
+	for (int t = 0; t < tps; ++t)
+	{
+		u32 c = h[t * 256 + d];
+		h[t * 256 + d] = run;
+		run += c;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+scatter_kernel(const u32 *__restrict__ kin, const u32 *__restrict__ iin, u32 *__restrict__ kout, u32 *__restrict__ iout,
+               const u32 *__restrict__ offs, int64_t n, int l, int tps, int shift)
+{
+	constexpr int kWarps = 8, kIters = kTile / (kWarps * 32);
+	__shared__ u32 wcnt[kWarps][256];
+	for (int i = threadIdx.x; i < kWarps * 256; i += 256) (&wcnt[0][0])[i] = 0;
+	__syncthreads();
+	TileRange r = tile_range(n, l, tps);
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const u32 lt_mask = (1u << lane) - 1u;
+	u32 key[kIters], id[kIters], rank[kIters];
+#pragma unroll
+	for (int it = 0; it < kIters; ++it)
+	{
+		int64_t j = r.a + (int64_t)w * (kTile / kWarps) + it * 32 + lane;
+		bool valid = j < r.b;
+		key[it] = valid ? kin[j] : 0u;
+		id[it] = valid ? iin[j] : 0u;
+		u32 dg = valid ? ((key[it] >> shift) & 255u) : (256u + lane);
+		u32 peers = __match_any_sync(0xffffffffu, dg);
+		u32 prior = valid ? wcnt[w][dg] : 0u;
+		rank[it] = prior + __popc(peers & lt_mask);
+		__syncwarp();
+		if (valid && lane == __ffs(peers) - 1) wcnt[w][dg] = prior + __popc(peers);
+		__syncwarp();
+	}
+	__syncthreads();
+	{
+		const int d = threadIdx.x;
+		u32 run = offs[(int64_t)blockIdx.x * 256 + d];
+#pragma unroll
+		for (int ww = 0; ww < kWarps; ++ww) { u32 c = wcnt[ww][d]; wcnt[ww][d] = run; run += c; }
+	}
+	__syncthreads();
+#pragma unroll
+	for (int it = 0; it < kIters; ++it)
+	{
+		int64_t j = r.a + (int64_t)w * (kTile / kWarps) + it * 32 + lane;
+		if (j < r.b)
+		{
+			u32 dst = wcnt[w][(key[it] >> shift) & 255u] + rank[it];
+			kout[dst] = key[it];
+			iout[dst] = id[it];
+		}
+	}
+}
+
+// final order when every level was a top level: perm = id, spos = pos[id]
+__global__ void __launch_bounds__(256)
+gather_sorted_kernel(const float *__restrict__ pos, const u32 *__restrict__ idx, float *__restrict__ spos, int *__restrict__ perm, int64_t n)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+	{
+		u32 id = idx[j];
+		perm[j] = (int)id;
+		spos[3*j] = pos[3*(int64_t)id]; spos[3*j+1] = pos[3*(int64_t)id+1]; spos[3*j+2] = pos[3*(int64_t)id+2];
+	}
+}
+
+// =====================================================================================
+//  bottom levels: one CTA per level-lt node, particles resident in shared memory
+// =====================================================================================
+struct BottomSmem
+{
+	float *sx, *sy, *sz;
+	u64 *comp;
+};
+
+__device__ __forceinline__ float slot_coord(const BottomSmem &s, int axis, u32 slot)
+{
+	return axis == 0 ? s.sx[slot] : (axis == 1 ? s.sy[slot] : s.sz[slot]);
+}
+
+// strict "a before b" in the order a stable sort on the split axis would produce
+__device__ __forceinline__ bool comp_less(u64 a, u64 b, const BottomSmem &s, int chain, const u32 *__restrict__ idx_in, int64_t s0)
+{
+	u64 ka = a >> 13, kb = b >> 13;
+	if (ka != kb) return ka < kb;
+	if (a == ~0ull) return false;
+	u32 sa = (u32)a & kSlotMask, sb = (u32)b & kSlotMask;
+	for (int c = 1; c < 3; ++c)
+	{
+		int ax = (chain >> (2 * c)) & 3;
+		if (ax == kNoAxis) break;
+		u32 ua = ordered_bits(slot_coord(s, ax, sa)), ub = ordered_bits(slot_coord(s, ax, sb));
+		if (ua != ub) return ua < ub;
+	}
+	u32 ia = idx_in ? idx_in[s0 + sa] : sa, ib = idx_in ? idx_in[s0 + sb] : sb;
+	return ia < ib;
+}
+
+__global__ void __launch_bounds__(kBottomThreads, 1)
+kd_bottom_kernel(TreeGeom g, const float *__restrict__ pos, const u32 *__restrict__ idx_in,
+                 float *__restrict__ spos, int *__restrict__ perm, int64_t n, int lt, int L, int P2)
+{
+	extern __shared__ unsigned char smem_raw[];
+	BottomSmem s;
+	s.comp = reinterpret_cast<u64 *>(smem_raw);
+	s.sx = reinterpret_cast<float *>(smem_raw + sizeof(u64) * kBottomCap);
+	s.sy = s.sx + kBottomCap;
+	s.sz = s.sy + kBottomCap;
+	const int tid = threadIdx.x;
+	const int b = blockIdx.x;
+	const int64_t s0 = seg_start(n, b, lt);
+	const int c0 = (int)(seg_start(n, b + 1, lt) - s0);
+
+	for (int t = tid; t < c0; t += kBottomThreads)
+	{
+		int64_t id = idx_in ? (int64_t)idx_in[s0 + t] : s0 + t;
+		s.sx[t] = pos[3*id]; s.sy[t] = pos[3*id+1]; s.sz[t] = pos[3*id+2];
+	}
+	__syncthreads();
+
+	const int nlev = L - lt; // sorting levels lt .. L-1
+	for (int j = 0; j < nlev; ++j)
+	{
+		const int l = lt + j;
+		const int B = P2 >> j, logB = 31 - __clz(B);
+		// (a) composite words (key << 13 | slot) of every block, padded with ~0
+		for (int p = tid; p < P2; p += kBottomThreads)
+		{
+			int q = p >> logB, t = p & (B - 1);
+			int64_t i = ((int64_t)b << j) + q;
+			int cnt = (int)(seg_start(n, i + 1, l) - seg_start(n, i, l));
+			u64 c = ~0ull;
+			if (t < cnt)
+			{
+				u32 slot = (j == 0) ? (u32)t : ((u32)s.comp[p] & kSlotMask);
+				int axis = g.splitdim[kd_beg(l) + (int)i];
+				c = ((u64)ordered_bits(slot_coord(s, axis, slot)) << 13) | slot;
+			}
+			s.comp[p] = c;
+		}
+		__syncthreads();
+		// (b) bitonic sort inside every block of B words
+		for (int k = 2; k <= B; k <<= 1)
+			for (int jj = k >> 1; jj > 0; jj >>= 1)
+			{
+				for (int t = tid; t < (P2 >> 1); t += kBottomThreads)
+				{
+					int lo = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+					int hi = lo | jj;
+					bool asc = (lo & k) == 0 || k == B;
+					// inside a block the final merge (k == B) is ascending for every block
+					u64 a = s.comp[lo], c = s.comp[hi];
+					int chain = 0;
+					bool tie = (a >> 13) == (c >> 13) && a != ~0ull;
+					if (tie) chain = g.chain[kd_beg(l) + (int)(((int64_t)b << j) + (lo >> logB))];
+					bool sw = asc ? comp_less(c, a, s, chain, idx_in, s0) : comp_less(a, c, s, chain, idx_in, s0);
+					if (sw) { s.comp[lo] = c; s.comp[hi] = a; }
+				}
+				__syncthreads();
+			}
+		// (c) boxes of the children (evalBox_krnl for level l+1)
+		for (int q = tid; q < (1 << j); q += kBottomThreads)
+		{
+			int64_t i = ((int64_t)b << j) + q;
+			int node = kd_beg(l) + (int)i;
+			int kl = (int)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
+			int axis = g.splitdim[node], pch = g.chain[node];
+			float lb[3], rb[3];
+			for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
+			float cl = slot_coord(s, axis, (u32)s.comp[q * B + kl - 1] & kSlotMask);
+			float cr = slot_coord(s, axis, (u32)s.comp[q * B + kl] & kSlotMask);
+			float save = rb[axis];
+			rb[axis] = cl;
+			write_box(g, 2*node + 1, lb, rb, pch);
+			rb[axis] = save; lb[axis] = cr;
+			write_box(g, 2*node + 2, lb, rb, pch);
+		}
+		if (j + 1 < nlev)
+		{
+			// (d) move every right child to the start of the second half of its parent's block
+			constexpr int kPer = kBottomCap / kBottomThreads;
+			u64 v[kPer];
+			const int Bh = B >> 1, logBh = logB - 1;
+#pragma unroll
+			for (int e = 0; e < kPer; ++e)
+			{
+				int p = tid + e * kBottomThreads;
+				v[e] = ~0ull;
+				if (p < P2)
+				{
+					int q2 = p >> logBh, t = p & (Bh - 1), q = q2 >> 1;
+					int64_t i2 = ((int64_t)b << (j + 1)) + q2;
+					int cnt = (int)(seg_start(n, i2 + 1, l + 1) - seg_start(n, i2, l + 1));
+					int kl = (int)(seg_start(n, (i2 | 1), l + 1) - seg_start(n, (i2 & ~1ll), l + 1));
+					if (t < cnt) v[e] = s.comp[q * B + ((q2 & 1) ? kl + t : t)];
+				}
+			}
+			__syncthreads();
+#pragma unroll
+			for (int e = 0; e < kPer; ++e)
+			{
+				int p = tid + e * kBottomThreads;
+				if (p < P2) s.comp[p] = v[e];
+			}
+		}
+		__syncthreads();
+	}
+	// output: storage order = order after the level-(L-1) sort
+	{
+		const int j = nlev - 1, l = L - 1;
+		const int B = P2 >> j, logB = 31 - __clz(B);
+		for (int p = tid; p < P2; p += kBottomThreads)
+		{
+			int q = p >> logB, t = p & (B - 1);
+			int64_t i = ((int64_t)b << j) + q;
+			int64_t st = seg_start(n, i, l);
+			int cnt = (int)(seg_start(n, i + 1, l) - st);
+			if (t < cnt)
+			{
+				u32 slot = (u32)s.comp[p] & kSlotMask;
+				int64_t dst = st + t;
+				perm[dst] = idx_in ? (int)idx_in[s0 + slot] : (int)(s0 + slot);
+				spos[3*dst] = s.sx[slot]; spos[3*dst+1] = s.sy[slot]; spos[3*dst+2] = s.sz[slot];
+			}
+		}
+	}
+}
+
+// =====================================================================================
+//  permutation glue (replaces the gather_krnl/copy_krnl pairs, kernel.cuh:228-311)
+// =====================================================================================
+__global__ void __launch_bounds__(256) gather3_kernel(const float *__restrict__ src, const int *__restrict__ perm, float *__restrict__ dst, int64_t n)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+	{
+		int64_t s = perm[j];
+		dst[3*j] = src[3*s]; dst[3*j+1] = src[3*s+1]; dst[3*j+2] = src[3*s+2];
+	}
+}
+
+// =====================================================================================
+//  dual tree traversal, level-synchronous (replaces fmm_dualTraversal, :429-567)
+// =====================================================================================
+struct TravArgs
+{
+	const float4 *center;
+	const float *size2;
+	const float *mfac;    // [level][2]: MAC factor M for the low / high multiplicity of the level
+	int2 *p2p, *m2l, *front_in, *front_out;
+	u32 *cnt;             // [0] p2p, [1] m2l, [2..4] frontier sizes (rotating)
+	u32 cap_p2p, cap_m2l, cap_front;
+	int64_t n;
+	int ntot, L, m2l_first;
+	float radius;
+};
+
+__device__ __forceinline__ int node_mult(int64_t n, int node, int &level)
+{
+	level = node_level(node);
+	int i = node - kd_beg(level);
+	return (int)(seg_start(n, i + 1, level) - seg_start(n, i, level));
+}
+
+// kd_admissible (:401-414) with the host's operation order; pow() comes from the host table
+__device__ __forceinline__ bool mac_ok(const TravArgs &a, int n1, int n2)
+{
+	float4 c1 = a.center[n1], c2 = a.center[n2];
+	float dx = __fsub_rn(c2.x, c1.x), dy = __fsub_rn(c2.y, c1.y), dz = __fsub_rn(c2.z, c1.z);
+	float dist2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+	float sz = fmaxf(a.size2[n1], a.size2[n2]);
+	int l1, l2;
+	int m1 = node_mult(a.n, n1, l1), m2 = node_mult(a.n, n2, l2);
+	int lv = m1 >= m2 ? l1 : l2, mm = m1 >= m2 ? m1 : m2;
+	float M = a.mfac[2 * lv + (mm != (int)(a.n >> lv))];
+	float parM = __fmul_rn(a.radius, M);
+	return __fmul_rn(__fmul_rn(parM, parM), sz) < dist2;
+}
+
+// append `count` items per lane with one atomic per warp; returns this lane's first slot
+__device__ __forceinline__ u32 warp_append(u32 *counter, int count)
+{
+	const int lane = threadIdx.x & 31;
+	int incl = count;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		int v = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += v;
+	}
+	int total = __shfl_sync(0xffffffffu, incl, 31);
+	u32 base = 0;
+	if (lane == 31 && total > 0) base = atomicAdd(counter, (u32)total);
+	base = __shfl_sync(0xffffffffu, base, 31);
+	return base + (u32)(incl - count);
+}
+
+__global__ void __launch_bounds__(256) traverse_round_kernel(TravArgs a, int round)
+{
+	u32 *cin = a.cnt + 2 + round % 3, *cout = a.cnt + 2 + (round + 1) % 3, *cnext = a.cnt + 2 + (round + 2) % 3;
+	if (blockIdx.x == 0 && threadIdx.x == 0) *cnext = 0; // nobody touches it during this round
+	const u32 nin = min(*cin, a.cap_front);
+	const u32 nwork = (nin + 31u) & ~31u; // whole warps stay converged for the shuffles
+	for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += gridDim.x * blockDim.x)
+	{
+		int kind = 0; // 0 nothing, 1 p2p, 2 m2l, 3 self split, 4 split y, 5 split x
+		int2 np = make_int2(0, 0);
+		if (w < nin)
+		{
+			np = a.front_in[w];
+			const bool xl = 2*np.x + 1 >= a.ntot, yl = 2*np.y + 1 >= a.ntot;
+			if (!a.m2l_first && xl && yl) kind = (np.x != np.y) ? 1 : 0;
+			else if (np.x == np.y && !xl) kind = 3;
+			else if (np.x != np.y && mac_ok(a, np.x, np.y)) kind = 2;
+			else if (xl && yl) kind = (np.x != np.y) ? 1 : 0;
+			else if (xl || (!yl && a.size2[np.x] <= a.size2[np.y])) kind = 4;
+			else kind = 5;
+		}
+		u32 s1 = warp_append(a.cnt + 0, kind == 1);
+		if (kind == 1 && s1 < a.cap_p2p) a.p2p[s1] = np;
+		u32 s2 = warp_append(a.cnt + 1, kind == 2);
+		if (kind == 2 && s2 < a.cap_m2l) a.m2l[s2] = np;
+		int nf = kind == 3 ? 3 : (kind >= 4 ? 2 : 0);
+		u32 s3 = warp_append(cout, nf);
+		if (nf && s3 + nf > a.cap_front) a.cnt[5] = 1u; // sticky: a frontier did not fit
+		if (nf && s3 + nf <= a.cap_front)
+		{
+			if (kind == 3)
+			{
+				a.front_out[s3]     = make_int2(2*np.x + 1, 2*np.x + 1);
+				a.front_out[s3 + 1] = make_int2(2*np.x + 1, 2*np.x + 2);
+				a.front_out[s3 + 2] = make_int2(2*np.x + 2, 2*np.x + 2);
+			}
+			else if (kind == 4)
+			{
+				a.front_out[s3]     = make_int2(np.x, 2*np.y + 1);
+				a.front_out[s3 + 1] = make_int2(np.x, 2*np.y + 2);
+			}
+			else
+			{
+				a.front_out[s3]     = make_int2(2*np.x + 1, np.y);
+				a.front_out[s3 + 1] = make_int2(2*np.x + 2, np.y);
+			}
+		}
+	}
+}
+
+__global__ void traverse_init_kernel(int2 *front, u32 *cnt)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0)
+	{
+		front[0] = make_int2(0, 0);
+		cnt[0] = 0; cnt[1] = 0; cnt[2] = 1; cnt[3] = 0; cnt[4] = 0; cnt[5] = 0;
+	}
+}
+
+// =====================================================================================
+//  near field (replaces fmm_p2p3_kdtree_coalesced / _self_, :874-959,1048-1120)
+// =====================================================================================
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+	float y;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+	return y;
+}
+
+// a group of G lanes handles one leaf pair (both directions) or one leaf against itself
+template <int G, bool SELF>
+__global__ void __launch_bounds__(256)
+p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap, const float *__restrict__ spos,
+           float *__restrict__ acc, int64_t n, int L, float eps2)
+{
+	const int lane = threadIdx.x & (G - 1);
+	const int groups = (gridDim.x * blockDim.x) / G;
+	const int beg = kd_beg(L);
+	const u32 npairs = SELF ? (1u << L) : min(*count, cap);
+	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+	const u32 nwork = ((npairs + (32 / G) - 1) / (32 / G)) * (32 / G); // keep whole warps in the loop
+	for (u32 w = (blockIdx.x * blockDim.x + threadIdx.x) / G; w < nwork; w += groups)
+	{
+		if (w >= npairs) continue;
+		int l1, l2;
+		if (SELF) { l1 = l2 = (int)w; }
+		else { int2 np = list[w]; l1 = np.x - beg; l2 = np.y - beg; }
+		const int64_t i1 = seg_start(n, l1, L), i2 = seg_start(n, l2, L);
+		const int m1 = (int)(seg_start(n, l1 + 1, L) - i1), m2 = (int)(seg_start(n, l2 + 1, L) - i2);
+#pragma unroll 1
+		for (int dir = 0; dir < (SELF ? 1 : 2); ++dir)
+		{
+			const int64_t ti = dir ? i2 : i1, si = dir ? i1 : i2;
+			const int tm = dir ? m2 : m1, sm = dir ? m1 : m2;
+			for (int h0 = 0; h0 < tm; h0 += G)
+			{
+				const int h = h0 + lane;
+				const bool hv = h < tm;
+				const float *tp = spos + 3 * (ti + (hv ? h : 0));
+				const float x = tp[0], y = tp[1], z = tp[2];
+				float ax = 0.f, ay = 0.f, az = 0.f;
+				for (int g0 = 0; g0 < sm; g0 += G)
+				{
+					const int gl = g0 + lane;
+					const float *sp = spos + 3 * (si + (gl < sm ? gl : 0));
+					const float sx = sp[0], sy = sp[1], sz = sp[2];
+					const int ng = min(G, sm - g0);
+					for (int g = 0; g < ng; ++g)
+					{
+						float dx = x - __shfl_sync(gmask, sx, g, G);
+						float dy = y - __shfl_sync(gmask, sy, g, G);
+						float dz = z - __shfl_sync(gmask, sz, g, G);
+						float r2 = fmaf(dx, dx, eps2);
+						r2 = fmaf(dy, dy, r2);
+						r2 = fmaf(dz, dz, r2);
+						float wv = rsqrt_approx(r2);
+						float w3 = (wv * wv) * wv;
+						ax = fmaf(dx, w3, ax); ay = fmaf(dy, w3, ay); az = fmaf(dz, w3, az);
+					}
+				}
+				if (hv)
+				{
+					float *o = acc + 3 * (ti + h);
+					atomicAdd(o, ax); atomicAdd(o + 1, ay); atomicAdd(o + 2, az);
+				}
+			}
+		}
+	}
+}
+
+} // namespace
+
+// =====================================================================================
+//  host side: plan, phases, introspection
+// =====================================================================================
+enum Phase { PH_BUILD = 0, PH_UPWARD, PH_TRAVERSE, PH_P2P, PH_M2L, PH_DOWNWARD, PH_COUNT };
+static const char *kPhaseNames[PH_COUNT] = {"kd_build", "p2m_m2m", "traverse", "p2p", "m2l", "l2l_l2p"};
+
+struct FmmPlan
+{
+	int64_t n = 0;
+	int L = 0, lt = 0, ntot = 0, order = 0, offM = 0, offL = 0, sM = 0, sL = 0, mlt_max = 0;
+	int counter = 0, rebuilt = 0, max_level = -1;
+	float dens = 0.f;
+	int64_t p2p_n = 0, m2l_n = 0;
+	u32 cap_list = 0, cap_front = 0;
+	DevBuf lbound, rbound, size2, splitdim, chain, center, mpole, local;
+	DevBuf keysA, keysB, idxA, idxB, hist, spos, perm, tmp3, accn;
+	DevBuf p2p, m2l, frontA, frontB, cnt, bbox, mfac;
+	cudaEvent_t ev[PH_COUNT + 1];
+	bool ev_ok = false, ev_valid = false;
+	bool bottom_attr = false;
+};
+
+static int plan_levels(int64_t n, int order, float dens, int max_level)
+{
+	// fmm_cart3_kdtree.cuh:1507-1516
+	float s = (float)(order * order);
+	int L = max_level == 0 ? (int)std::round(std::log2(dens * (float)n / s)) : max_level;
+	L = std::min(std::max(L, 2), 30);
+	while ((1ll << L) > n) --L;
+	return L;
+}
+
+static int ensure_plan(nbco_ctx *ctx, int64_t n)
+{
+	const nbco_config &c = ctx->cfg;
+	if (!ctx->fmm) ctx->fmm = new FmmPlan();
+	FmmPlan &p = *ctx->fmm;
+	if (!p.ev_ok)
+	{
+		for (int i = 0; i <= PH_COUNT; ++i) NBCO_CUDA(cudaEventCreate(&p.ev[i]));
+		p.ev_ok = true;
+	}
+	if (p.n == n && p.order == c.order && p.dens == c.dens_inhom && p.max_level == c.max_level) return NBCO_OK;
+	if (n < 8) { set_error("fmm3_kd needs n >= 8 (got %lld)", (long long)n); return NBCO_ERR_INVALID; }
+	if (n >= (1ll << 31)) { set_error("n must be < 2^31"); return NBCO_ERR_INVALID; }
+	const int L = plan_levels(n, c.order, c.dens_inhom, c.max_level);
+	if (L < 1) { set_error("tree depth %d", L); return NBCO_ERR_INVALID; }
+	p.n = n; p.order = c.order; p.dens = c.dens_inhom; p.max_level = c.max_level;
+	p.L = L; p.ntot = (1 << (L + 1)) - 1;
+	p.offM = c.order * (c.order + 1) * (c.order + 2) / 6; p.offL = (c.order + 1) * (c.order + 1);
+	p.sM = (p.offM + 3) & ~3; p.sL = (p.offL + 3) & ~3;
+	p.mlt_max = (int)((n - 1) / (1ll << L) + 1);
+	p.counter = 0;
+	// first level whose segments fit a bottom CTA
+	int lt = 0;
+	while (((n - 1) >> lt) + 1 > kBottomCap) ++lt;
+	p.lt = lt;
+	const size_t nt = (size_t)p.ntot;
+	NBCO_TRY(p.lbound.reserve(12 * nt)); NBCO_TRY(p.rbound.reserve(12 * nt)); NBCO_TRY(p.size2.reserve(4 * nt));
+	NBCO_TRY(p.splitdim.reserve(4 * nt)); NBCO_TRY(p.chain.reserve(4 * nt)); NBCO_TRY(p.center.reserve(16 * nt));
+	NBCO_TRY(p.mpole.reserve(4 * nt * p.sM)); NBCO_TRY(p.local.reserve(4 * nt * p.sL));
+	NBCO_TRY(p.keysA.reserve(4 * (size_t)n)); NBCO_TRY(p.keysB.reserve(4 * (size_t)n));
+	NBCO_TRY(p.idxA.reserve(4 * (size_t)n)); NBCO_TRY(p.idxB.reserve(4 * (size_t)n));
+	NBCO_TRY(p.spos.reserve(12 * (size_t)n)); NBCO_TRY(p.perm.reserve(4 * (size_t)n));
+	NBCO_TRY(p.tmp3.reserve(12 * (size_t)n)); NBCO_TRY(p.accn.reserve(12 * (size_t)n));
+	const size_t tiles = (size_t)((n + kTile - 1) / kTile) + (1u << std::min(lt, L)) + 1;
+	NBCO_TRY(p.hist.reserve(4 * 256 * tiles));
+	if (p.cap_list < (u32)std::min<int64_t>(8ll * p.ntot + 1024, 0x7fffffff))
+	{
+		p.cap_list = (u32)std::min<int64_t>(8ll * p.ntot + 1024, 0x7fffffff);
+		p.cap_front = p.cap_list;
+	}
+	NBCO_TRY(p.p2p.reserve(8 * (size_t)p.cap_list)); NBCO_TRY(p.m2l.reserve(8 * (size_t)p.cap_list));
+	NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
+	NBCO_TRY(p.cnt.reserve(64)); NBCO_TRY(p.bbox.reserve(64)); NBCO_TRY(p.mfac.reserve(4 * 2 * 40));
+	// MAC factor table: M = pow(mult / N, 1/(3p+6)) evaluated with the host libm like the
+	// reference CPU path (:410); a node of level l holds floor(n/2^l) or floor(n/2^l)+1 particles
+	float tab[2 * 32];
+	for (int l = 0; l <= L; ++l)
+	{
+		int lo = (int)(n >> l);
+		tab[2*l]     = powf((float)lo / (float)(int)n, 1.f / (3 * c.order + 6));
+		tab[2*l + 1] = powf((float)(lo + 1) / (float)(int)n, 1.f / (3 * c.order + 6));
+	}
+	NBCO_CUDA(cudaMemcpyAsync(p.mfac.p, tab, sizeof(float) * 2 * (L + 1), cudaMemcpyHostToDevice, ctx->stream));
+	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
+	return NBCO_OK;
+}
+
+#define LAUNCHED(ctx) do { ++(ctx)->launches; } while (0)
+
+static int build_tree(nbco_ctx *ctx, FmmPlan &p, const float *pos)
+{
+	cudaStream_t st = ctx->stream;
+	const int64_t n = p.n;
+	TreeGeom g{p.lbound.as<float>(), p.rbound.as<float>(), p.size2.as<float>(), p.splitdim.as<int>(), p.chain.as<int>()};
+	u32 *bb = p.bbox.as<u32>();
+	static const u32 bb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+	NBCO_CUDA(cudaMemcpyAsync(bb, bb_init, sizeof(bb_init), cudaMemcpyHostToDevice, st));
+	bbox_kernel<<<grid_for(n, 256, ctx->sm_count, 4), 256, 0, st>>>(pos, n, bb); LAUNCHED(ctx);
+	root_box_kernel<<<1, 32, 0, st>>>(g, bb); LAUNCHED(ctx);
+
+	u32 *kA = p.keysA.as<u32>(), *kB = p.keysB.as<u32>(), *iA = p.idxA.as<u32>(), *iB = p.idxB.as<u32>();
+	u32 *hist = p.hist.as<u32>();
+	const int ltop = std::min(p.lt, p.L); // levels [0, ltop) are sorted globally
+	for (int l = 0; l < ltop; ++l)
+	{
+		const int nseg = 1 << l;
+		const int64_t maxseg = ((n - 1) >> l) + 1;
+		const int tps = (int)((maxseg + kTile - 1) / kTile);
+		const int tiles = nseg * tps;
+		if (l > 0) { evalbox_top_kernel<<<(nseg + 255) / 256, 256, 0, st>>>(g, kA, n, l); LAUNCHED(ctx); }
+		keygen_hist_kernel<<<tiles, 256, 0, st>>>(pos, g.splitdim, l == 0 ? nullptr : iA, kA, iA, hist, n, l, tps); LAUNCHED(ctx);
+		for (int pass = 0; pass < 4; ++pass)
+		{
+			u32 *kin = (pass & 1) ? kB : kA, *iin = (pass & 1) ? iB : iA;
+			u32 *kout = (pass & 1) ? kA : kB, *iout = (pass & 1) ? iA : iB;
+			if (pass > 0) { hist_kernel<<<tiles, 256, 0, st>>>(kin, hist, n, l, tps, 8 * pass); LAUNCHED(ctx); }
+			seg_scan_kernel<<<nseg, 256, 0, st>>>(hist, n, l, tps); LAUNCHED(ctx);
+			scatter_kernel<<<tiles, 256, 0, st>>>(kin, iin, kout, iout, hist, n, l, tps, 8 * pass); LAUNCHED(ctx);
+		}
+	}
+	if (ltop > 0) { evalbox_top_kernel<<<((1 << ltop) + 255) / 256, 256, 0, st>>>(g, kA, n, ltop); LAUNCHED(ctx); }
+	if (ltop < p.L)
+	{
+		const size_t smem = (sizeof(u64) + 3 * sizeof(float)) * kBottomCap;
+		if (!p.bottom_attr)
+		{
+			NBCO_CUDA(cudaFuncSetAttribute(kd_bottom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			p.bottom_attr = true;
+		}
+		int64_t maxseg = ((n - 1) >> ltop) + 1;
+		int P2 = 2; while (P2 < maxseg) P2 <<= 1;
+		// the sort needs at least 2 words per block down to the last level
+		while ((P2 >> (p.L - 1 - ltop)) < 2) P2 <<= 1;
+		if (P2 > kBottomCap) { set_error("internal: bottom block %d", P2); return NBCO_ERR_INVALID; }
+		kd_bottom_kernel<<<1 << ltop, kBottomThreads, smem, st>>>(g, pos, ltop == 0 ? nullptr : iA, p.spos.as<float>(),
+		                                                         p.perm.as<int>(), n, ltop, p.L, P2);
+		LAUNCHED(ctx);
+	}
+	else
+	{
+		gather_sorted_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(pos, iA, p.spos.as<float>(), p.perm.as<int>(), n);
+		LAUNCHED(ctx);
+	}
+	NBCO_CUDA(cudaGetLastError());
+	return NBCO_OK;
+}
+
+static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_pos, float *d_acc, const float *d_param, bool fuse_elastic, bool rebuild)
+{
+	cudaStream_t st = ctx->stream;
+	const int64_t n = p.n;
+	const int L = p.L;
+	const nbco_config &c = ctx->cfg;
+	TreeData t{p.center.as<float4>(), p.mpole.as<float>(), p.local.as<float>(), p.sM, p.sL};
+
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_BUILD], st));
+	const float *spos = d_pos; // tree-ordered positions the passes read
+	if (rebuild)
+	{
+		NBCO_TRY(build_tree(ctx, p, d_pos));
+		if (c.unsort)
+			spos = p.spos.as<float>();
+		else
+		{
+			// leave pos and the velocities behind it in tree order (:1359-1360,1758-1759)
+			NBCO_CUDA(cudaMemcpyAsync(d_pos, p.spos.p, 12 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+			gather3_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(d_pos + 3*n, p.perm.as<int>(), p.tmp3.as<float>(), n); LAUNCHED(ctx);
+			NBCO_CUDA(cudaMemcpyAsync(d_pos + 3*n, p.tmp3.p, 12 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+		}
+	}
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_UPWARD], st));
+	NBCO_CUDA(cudaMemsetAsync(p.local.p, 0, sizeof(float) * (size_t)p.ntot * p.sL, st));
+	ops.upward(ctx, t, spos, n, L);
+
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_TRAVERSE], st));
+	TravArgs a;
+	a.center = t.center; a.size2 = p.size2.as<float>(); a.mfac = p.mfac.as<float>();
+	a.p2p = p.p2p.as<int2>(); a.m2l = p.m2l.as<int2>();
+	a.cnt = p.cnt.as<u32>();
+	a.cap_p2p = a.cap_m2l = p.cap_list; a.cap_front = p.cap_front;
+	a.n = n; a.ntot = p.ntot; a.L = L; a.m2l_first = c.m2l_first; a.radius = c.radius;
+	traverse_init_kernel<<<1, 32, 0, st>>>(p.frontA.as<int2>(), a.cnt); LAUNCHED(ctx);
+	const int rounds = 2 * L + 2;
+	for (int r = 0; r < rounds; ++r)
+	{
+		a.front_in = (r & 1) ? p.frontB.as<int2>() : p.frontA.as<int2>();
+		a.front_out = (r & 1) ? p.frontA.as<int2>() : p.frontB.as<int2>();
+		traverse_round_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, r); LAUNCHED(ctx);
+	}
+
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_P2P], st));
+	float *accn = p.accn.as<float>();
+	NBCO_CUDA(cudaMemsetAsync(accn, 0, 12 * (size_t)n, st));
+	if (c.coll)
+	{
+		const int blocks = ctx->sm_count * 8;
+#define P2P_LAUNCH(G)                                                                                              \
+		do {                                                                                                       \
+			p2p_kernel<G, false><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2);   \
+			p2p_kernel<G, true><<<blocks, 256, 0, st>>>(nullptr, nullptr, 0, spos, accn, n, L, c.eps2);            \
+		} while (0)
+		if (p.mlt_max <= 4) P2P_LAUNCH(4);
+		else if (p.mlt_max <= 8) P2P_LAUNCH(8);
+		else if (p.mlt_max <= 16) P2P_LAUNCH(16);
+		else P2P_LAUNCH(32);
+#undef P2P_LAUNCH
+		ctx->launches += 2;
+	}
+
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_M2L], st));
+	ops.m2l(ctx, t, a.m2l, a.cnt + 1, a.cap_m2l, c.eps2);
+
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_DOWNWARD], st));
+	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L);
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_COUNT], st));
+	NBCO_CUDA(cudaGetLastError());
+	return NBCO_OK;
+}
+
+int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const float *d_param, bool fuse_elastic)
+{
+	if (ctx->cfg.world != 1) { set_error("fmm3_kd: multi-GPU sharding is not available yet"); return NBCO_ERR_INVALID; }
+	NBCO_TRY(ensure_plan(ctx, n));
+	FmmPlan &p = *ctx->fmm;
+	const bool rebuild = ctx->cfg.unsort || (p.counter % ctx->cfg.tree_steps == 0);
+	bool do_build = rebuild;
+	for (int attempt = 0; attempt < 6; ++attempt)
+	{
+		const OrderOps *ops = order_ops(p.order);
+		if (!ops) { set_error("order %d not instantiated", p.order); return NBCO_ERR_INVALID; }
+		int s = run_phases(*ops, ctx, p, d_pos, d_acc, d_param, fuse_elastic, do_build);
+		NBCO_TRY(s);
+		u32 h[6];
+		NBCO_CUDA(cudaMemcpyAsync(h, p.cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+		NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
+		p.ev_valid = true;
+		p.rebuilt = rebuild;
+		p.p2p_n = h[0]; p.m2l_n = h[1];
+		if (h[0] <= p.cap_list && h[1] <= p.cap_list && h[5] == 0)
+		{
+			++p.counter;
+			return NBCO_OK;
+		}
+		// a list or a frontier did not fit: grow and redo this evaluation.  With unsort == 0 the
+		// caller's arrays are already in tree order and the tree is valid: do not build again.
+		if (p.cap_list >= 0x7fffffffu / 2) break;
+		p.cap_list *= 2; p.cap_front = p.cap_list;
+		NBCO_TRY(p.p2p.reserve(8 * (size_t)p.cap_list)); NBCO_TRY(p.m2l.reserve(8 * (size_t)p.cap_list));
+		NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
+		if (!ctx->cfg.unsort) do_build = false;
+	}
+	set_error("interaction lists exceed capacity (%lld p2p, %lld m2l)", (long long)p.p2p_n, (long long)p.m2l_n);
+	return NBCO_ERR_OVERFLOW;
+}
+
+extern const OrderOps kOrderOps1, kOrderOps2, kOrderOps3, kOrderOps4, kOrderOps5, kOrderOps6;
+
+const OrderOps *order_ops(int order)
+{
+	switch (order)
+	{
+		case 1: return &kOrderOps1;
+		case 2: return &kOrderOps2;
+		case 3: return &kOrderOps3;
+		case 4: return &kOrderOps4;
+		case 5: return &kOrderOps5;
+		case 6: return &kOrderOps6;
+		default: return nullptr;
+	}
+}
+
+void fmm3_destroy(nbco_ctx *ctx)
+{
+	if (!ctx->fmm) return;
+	FmmPlan &p = *ctx->fmm;
+	DevBuf *all[] = {&p.lbound, &p.rbound, &p.size2, &p.splitdim, &p.chain, &p.center, &p.mpole, &p.local,
+	                 &p.keysA, &p.keysB, &p.idxA, &p.idxB, &p.hist, &p.spos, &p.perm, &p.tmp3, &p.accn,
+	                 &p.p2p, &p.m2l, &p.frontA, &p.frontB, &p.cnt, &p.bbox, &p.mfac};
+	for (DevBuf *b : all) b->release();
+	if (p.ev_ok) for (int i = 0; i <= PH_COUNT; ++i) cudaEventDestroy(p.ev[i]);
+	delete ctx->fmm;
+	ctx->fmm = nullptr;
+}
+
+} // namespace nbco
+
+using namespace nbco;
+
 extern "C" {
-int nbco_fmm_get_info(nbco_ctx *, nbco_fmm_info *) { return NBCO_ERR_INVALID; }
-int nbco_fmm_get_tree(nbco_ctx *, float *, float *, float *, float *, float *, int32_t *, int32_t *, int32_t *, int32_t *) { return NBCO_ERR_INVALID; }
-int nbco_fmm_get_lists(nbco_ctx *, int32_t *, int64_t, int32_t *, int64_t) { return NBCO_ERR_INVALID; }
-int nbco_fmm_get_phase_ms(nbco_ctx *, const char **, float *, int) { return 0; }
+
+int nbco_fmm_get_info(nbco_ctx *ctx, nbco_fmm_info *info)
+{
+	if (!ctx || !info || !ctx->fmm) { set_error("no FMM evaluation yet"); return NBCO_ERR_INVALID; }
+	FmmPlan &p = *ctx->fmm;
+	info->levels = p.L; info->order = p.order; info->n = p.n; info->nodes = p.ntot;
+	info->p2p_pairs = p.p2p_n; info->m2l_pairs = p.m2l_n; info->off_m = p.offM; info->off_l = p.offL;
+	info->rebuilt = p.rebuilt; info->mlt_max = p.mlt_max; info->kernel_launches = ctx->launches;
+	return NBCO_OK;
 }
+
+int nbco_fmm_get_tree(nbco_ctx *ctx, float *h_center, float *h_lbound, float *h_rbound, float *h_mpole, float *h_local,
+                      int32_t *h_mult, int32_t *h_index, int32_t *h_splitdim, int32_t *h_perm)
+{
+	if (!ctx || !ctx->fmm) { set_error("no FMM evaluation yet"); return NBCO_ERR_INVALID; }
+	NBCO_CUDA(cudaSetDevice(ctx->cfg.device));
+	FmmPlan &p = *ctx->fmm;
+	const size_t nt = (size_t)p.ntot;
+	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (h_lbound) NBCO_CUDA(cudaMemcpy(h_lbound, p.lbound.p, 12 * nt, cudaMemcpyDeviceToHost));
+	if (h_rbound) NBCO_CUDA(cudaMemcpy(h_rbound, p.rbound.p, 12 * nt, cudaMemcpyDeviceToHost));
+	if (h_splitdim) NBCO_CUDA(cudaMemcpy(h_splitdim, p.splitdim.p, 4 * nt, cudaMemcpyDeviceToHost));
+	if (h_perm) NBCO_CUDA(cudaMemcpy(h_perm, p.perm.p, 4 * (size_t)p.n, cudaMemcpyDeviceToHost));
+	if (h_center)
+	{
+		std::vector<float> tmp(4 * nt);
+		NBCO_CUDA(cudaMemcpy(tmp.data(), p.center.p, 16 * nt, cudaMemcpyDeviceToHost));
+		for (size_t i = 0; i < nt; ++i) { h_center[3*i] = tmp[4*i]; h_center[3*i+1] = tmp[4*i+1]; h_center[3*i+2] = tmp[4*i+2]; }
+	}
+	if (h_mpole)
+	{
+		std::vector<float> tmp(nt * p.sM);
+		NBCO_CUDA(cudaMemcpy(tmp.data(), p.mpole.p, 4 * nt * p.sM, cudaMemcpyDeviceToHost));
+		for (size_t i = 0; i < nt; ++i) memcpy(h_mpole + i * p.offM, tmp.data() + i * p.sM, 4 * (size_t)p.offM);
+	}
+	if (h_local)
+	{
+		std::vector<float> tmp(nt * p.sL);
+		NBCO_CUDA(cudaMemcpy(tmp.data(), p.local.p, 4 * nt * p.sL, cudaMemcpyDeviceToHost));
+		for (size_t i = 0; i < nt; ++i) memcpy(h_local + i * p.offL, tmp.data() + i * p.sL, 4 * (size_t)p.offL);
+	}
+	if (h_mult || h_index)
+		for (int l = 0; l <= p.L; ++l)
+			for (int64_t i = 0; i < (1ll << l); ++i)
+			{
+				int64_t s0 = seg_start(p.n, i, l), s1 = seg_start(p.n, i + 1, l);
+				if (h_index) h_index[kd_beg(l) + i] = (int32_t)s0;
+				if (h_mult) h_mult[kd_beg(l) + i] = (int32_t)(s1 - s0);
+			}
+	return NBCO_OK;
+}
+
+int nbco_fmm_get_lists(nbco_ctx *ctx, int32_t *h_p2p, int64_t p2p_cap, int32_t *h_m2l, int64_t m2l_cap)
+{
+	if (!ctx || !ctx->fmm) { set_error("no FMM evaluation yet"); return NBCO_ERR_INVALID; }
+	NBCO_CUDA(cudaSetDevice(ctx->cfg.device));
+	FmmPlan &p = *ctx->fmm;
+	if (p2p_cap < p.p2p_n || m2l_cap < p.m2l_n) { set_error("list buffers too small"); return NBCO_ERR_INVALID; }
+	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
+	auto fetch = [&](int32_t *dst, const DevBuf &src, int64_t cnt) -> int
+	{
+		if (!dst || cnt == 0) return NBCO_OK;
+		NBCO_CUDA(cudaMemcpy(dst, src.p, 8 * (size_t)cnt, cudaMemcpyDeviceToHost));
+		int2 *q = reinterpret_cast<int2 *>(dst);
+		std::sort(q, q + cnt, [](const int2 &a, const int2 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+		return NBCO_OK;
+	};
+	NBCO_TRY(fetch(h_p2p, p.p2p, p.p2p_n));
+	NBCO_TRY(fetch(h_m2l, p.m2l, p.m2l_n));
+	return NBCO_OK;
+}
+
+int nbco_fmm_get_phase_ms(nbco_ctx *ctx, const char **names, float *ms, int cap)
+{
+	if (!ctx || !ctx->fmm || !ctx->fmm->ev_valid) return 0;
+	FmmPlan &p = *ctx->fmm;
+	cudaSetDevice(ctx->cfg.device);
+	cudaStreamSynchronize(ctx->stream);
+	int k = 0;
+	for (; k < PH_COUNT && k < cap; ++k)
+	{
+		names[k] = kPhaseNames[k];
+		ms[k] = 0.f;
+		cudaEventElapsedTime(&ms[k], p.ev[k], p.ev[k + 1]);
+	}
+	return k;
+}
+
+} // extern "C"

@@ -1,0 +1,104 @@
+// fmm3_common.cuh -- types and index arithmetic shared by fmm3.cu (tree build, traversal, near
+// field, host driver) and the per-order operator translation units fmm3_p*.cu.
+#pragma once
+#include "common.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace nbco {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr int kTile = 4096;        // elements per radix tile (256 threads x 16)
+constexpr int kBottomCap = 8192;   // particles a bottom CTA keeps in shared memory
+constexpr int kBottomThreads = 1024;
+constexpr u32 kSlotMask = 0x1FFFu; // 13 bits: slot inside a bottom CTA
+constexpr int kNoAxis = 3;
+
+// ---- index arithmetic of the implicit tree (fmm_cart3_kdtree.cuh:33-78,117-118) ----
+__host__ __device__ __forceinline__ int kd_beg(int l) { return (1 << l) - 1; }
+__host__ __device__ __forceinline__ int64_t seg_start(int64_t n, int64_t i, int l)
+{
+	return i <= 0 ? 0 : (((n * i - 1) >> l) + 1); // ceil(n*i / 2^l)
+}
+__device__ __forceinline__ int node_level(int node) { return 31 - __clz(node + 1); }
+
+__host__ __device__ __forceinline__ u32 ordered_bits(float f)
+{
+#ifdef __CUDA_ARCH__
+	u32 u = __float_as_uint(f);
+#else
+	u32 u; memcpy(&u, &f, 4);
+#endif
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unordered_bits(u32 k)
+{
+	return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__device__ __forceinline__ int widest_axis(float dx, float dy, float dz)
+{
+	return (dx > dy) ? ((dx > dz) ? 0 : 2) : ((dy > dz) ? 1 : 2); // :92,129 (ties go to the later axis)
+}
+
+// kd_size (:395-399) with the host's operation order: (dx*dx + dy*dy) + dz*dz, no contraction
+__device__ __forceinline__ float box_size2(const float *lb, const float *rb)
+{
+	float dx = __fsub_rn(rb[0], lb[0]), dy = __fsub_rn(rb[1], lb[1]), dz = __fsub_rn(rb[2], lb[2]);
+	return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ int chain_push(int axis, int parent_chain)
+// axes in order of most recent use, without repeats; 2 bits each, 3 = none
+{
+	int c = axis, k = 1;
+	for (int s = 0; s < 3; ++s)
+	{
+		int a = (parent_chain >> (2 * s)) & 3;
+		if (a != kNoAxis && a != axis && k < 3) { c |= a << (2 * k); ++k; }
+	}
+	for (; k < 3; ++k) c |= kNoAxis << (2 * k);
+	return c;
+}
+
+struct TreeGeom
+{
+	float *lbound, *rbound;  // float3 per node
+	float *size2;            // kd_size per node
+	int *splitdim;           // widest axis per node
+	int *chain;              // tie-break chain per node
+};
+
+__device__ __forceinline__ void write_box(const TreeGeom &g, int node, const float *lb, const float *rb, int parent_chain)
+{
+	g.lbound[3*node] = lb[0]; g.lbound[3*node+1] = lb[1]; g.lbound[3*node+2] = lb[2];
+	g.rbound[3*node] = rb[0]; g.rbound[3*node+1] = rb[1]; g.rbound[3*node+2] = rb[2];
+	int ax = widest_axis(rb[0] - lb[0], rb[1] - lb[1], rb[2] - lb[2]);
+	g.splitdim[node] = ax;
+	g.chain[node] = chain_push(ax, parent_chain);
+	g.size2[node] = box_size2(lb, rb);
+}
+
+
+struct TreeData
+{
+	float4 *center;   // xyz, w unused
+	float *mpole;     // sM floats per node, symmetric tuple orders 0..P-1
+	float *local;     // sL floats per node, traceless tuple orders 0..P
+	int sM, sL;
+};
+
+// Order-specific passes (one translation unit per order: the unrolled templates are expensive
+// to compile, the reference's single TU takes > 4 min).
+struct OrderOps
+{
+	void (*upward)(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L);
+	void (*m2l)(nbco_ctx *ctx, TreeData t, const int2 *list, const unsigned *count, unsigned cap, float eps2);
+	void (*downward)(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
+	                 const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L);
+};
+const OrderOps *order_ops(int order);
+
+} // namespace nbco

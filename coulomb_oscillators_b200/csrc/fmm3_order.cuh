@@ -1,0 +1,257 @@
+// fmm3_order.cuh -- the order-templated passes of the kd-tree FMM (P2M, M2M, M2L, L2L, L2P) and
+// their launchers.  Included by fmm3_p<N>.cu, which instantiates exactly one order each.
+#pragma once
+#include "fmm3_common.cuh"
+#include "fmm_ops.cuh"
+
+namespace nbco {
+
+using namespace ops;
+
+namespace {
+
+// =====================================================================================
+//  upward pass
+// =====================================================================================
+// leaf centres (centerLeaves_krnl, appel.cuh:226-243: sequential fp32 mean) + P2M (:231-250)
+template <int P>
+__global__ void __launch_bounds__(128)
+leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L)
+{
+	const int m = 1 << L, beg = kd_beg(L);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+	{
+		int64_t st = seg_start(n, i, L);
+		int cnt = (int)(seg_start(n, i + 1, L) - st);
+		const float *p = spos + 3 * st;
+		float cx = 0.f, cy = 0.f, cz = 0.f;
+		for (int j = 0; j < cnt; ++j) { cx += p[3*j]; cy += p[3*j+1]; cz += p[3*j+2]; }
+		if (cnt > 0) { float f = (float)cnt; cx = __fdiv_rn(cx, f); cy = __fdiv_rn(cy, f); cz = __fdiv_rn(cz, f); }
+		t.center[beg + i] = make_float4(cx, cy, cz, 0.f);
+		float M[sym_off(P) > 0 ? sym_off(P) : 1];
+#pragma unroll
+		for (int k = 0; k < sym_off(P); ++k) M[k] = 0.f;
+		if constexpr (P >= 3)
+			for (int j = 0; j < cnt; ++j)
+				p2m_acc<P>(M, p[3*j] - cx, p[3*j+1] - cy, p[3*j+2] - cz);
+		M[0] = (float)cnt;
+		float *out = t.mpole + (int64_t)(beg + i) * t.sM;
+#pragma unroll
+		for (int k = 0; k < sym_off(P); ++k) out[k] = M[k];
+	}
+}
+
+// one parent from its two children (fmm_buildTree3_kdtree2_krnl, :328-368)
+template <int P>
+__device__ __forceinline__ void m2m_node(const TreeData &t, int node, int64_t n, int l, int i)
+{
+	const int c0 = 2*node + 1, c1 = c0 + 1;
+	const float m0 = (float)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
+	const float m1 = (float)(seg_start(n, 2*i + 2, l + 1) - seg_start(n, 2*i + 1, l + 1));
+	const float mt = (float)(seg_start(n, i + 1, l) - seg_start(n, i, l));
+	const float4 a = t.center[c0], b = t.center[c1];
+	// coord = (m0*c0 + m1*c1) / m with separately rounded products (host arithmetic, :345-348)
+	float cx = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.x), __fmul_rn(m1, b.x)), mt);
+	float cy = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.y), __fmul_rn(m1, b.y)), mt);
+	float cz = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.z), __fmul_rn(m1, b.z)), mt);
+	float M[sym_off(P) > 0 ? sym_off(P) : 1];
+#pragma unroll
+	for (int k = 0; k < sym_off(P); ++k) M[k] = 0.f;
+	if constexpr (P >= 3)
+	{
+		float Mi[sym_off(P)];
+		const float *s0 = t.mpole + (int64_t)c0 * t.sM, *s1 = t.mpole + (int64_t)c1 * t.sM;
+#pragma unroll
+		for (int k = 0; k < sym_off(P); ++k) Mi[k] = s0[k];
+		m2m_acc<P>(M, Mi, cx - a.x, cy - a.y, cz - a.z);
+#pragma unroll
+		for (int k = 0; k < sym_off(P); ++k) Mi[k] = s1[k];
+		m2m_acc<P>(M, Mi, cx - b.x, cy - b.y, cz - b.z);
+	}
+	M[0] = mt;
+	float *out = t.mpole + (int64_t)node * t.sM;
+#pragma unroll
+	for (int k = 0; k < sym_off(P); ++k) out[k] = M[k];
+	t.center[node] = make_float4(cx, cy, cz, 0.f);
+}
+
+template <int P>
+__global__ void __launch_bounds__(128) m2m_level_kernel(TreeData t, int64_t n, int l)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < (1 << l)) m2m_node<P>(t, kd_beg(l) + i, n, l, i);
+}
+
+// levels ltop .. 0 in one CTA (few nodes, dependent launches otherwise)
+template <int P>
+__global__ void __launch_bounds__(256) m2m_top_kernel(TreeData t, int64_t n, int ltop)
+{
+	for (int l = ltop; l >= 0; --l)
+	{
+		for (int i = threadIdx.x; i < (1 << l); i += blockDim.x)
+			m2m_node<P>(t, kd_beg(l) + i, n, l, i);
+		__syncthreads();
+	}
+}
+
+// =====================================================================================
+//  M2L (replaces fmm_c2c3_kdtree / _kdtree2, :613-750)
+// =====================================================================================
+template <int P>
+__global__ void __launch_bounds__(128)
+m2l_kernel(TreeData t, const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap, float eps2)
+{
+	const u32 npairs = min(*count, cap);
+	for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < npairs; w += gridDim.x * blockDim.x)
+	{
+		const int2 np = list[w];
+		const float4 c1 = t.center[np.x], c2 = t.center[np.y];
+		float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z;
+		const float r2 = dx*dx + dy*dy + dz*dz + eps2;
+		const float rinv = rsqrtf(r2);
+		dx *= rinv; dy *= rinv; dz *= rinv;
+		float M[sym_off(P)], Lq[trl_off(P + 1)];
+		// target np.x, source np.y
+		{
+			const float *src = t.mpole + (int64_t)np.y * t.sM;
+#pragma unroll
+			for (int k = 0; k < sym_off(P); ++k) M[k] = src[k];
+#pragma unroll
+			for (int k = 0; k < trl_off(P + 1); ++k) Lq[k] = 0.f;
+			m2l_acc<P>(Lq, M, dx, dy, dz, rinv);
+			float *dst = t.local + (int64_t)np.x * t.sL;
+#pragma unroll
+			for (int k = 1; k < trl_off(P + 1); ++k) atomicAdd(dst + k, Lq[k]);
+		}
+		// target np.y, source np.x
+		{
+			const float *src = t.mpole + (int64_t)np.x * t.sM;
+#pragma unroll
+			for (int k = 0; k < sym_off(P); ++k) M[k] = src[k];
+#pragma unroll
+			for (int k = 0; k < trl_off(P + 1); ++k) Lq[k] = 0.f;
+			m2l_acc<P>(Lq, M, -dx, -dy, -dz, rinv);
+			float *dst = t.local + (int64_t)np.y * t.sL;
+#pragma unroll
+			for (int k = 1; k < trl_off(P + 1); ++k) atomicAdd(dst + k, Lq[k]);
+		}
+	}
+}
+
+// =====================================================================================
+//  downward pass (replaces fmm_pushl3_kdtree*, fmm_pushLeaves3_kdtree*, rescale, add_elastic)
+// =====================================================================================
+template <int P>
+__device__ __forceinline__ void l2l_node(const TreeData &t, int child)
+{
+	const int parent = (child - 1) >> 1;
+	const float4 cp = t.center[parent], cc = t.center[child];
+	float Lp[trl_off(P + 1)], S[sym_off(P + 1)], Lc[trl_off(P + 1)];
+	const float *src = t.local + (int64_t)parent * t.sL;
+	float *dst = t.local + (int64_t)child * t.sL;
+#pragma unroll
+	for (int k = 0; k < trl_off(P + 1); ++k) { Lp[k] = src[k]; Lc[k] = dst[k]; }
+	S[0] = 0.f;
+	local_expand<P>(S, Lp);
+	l2l_acc<P>(Lc, S, cc.x - cp.x, cc.y - cp.y, cc.z - cp.z);
+#pragma unroll
+	for (int k = 1; k < trl_off(P + 1); ++k) dst[k] = Lc[k];
+}
+
+// children of level l (i.e. nodes of level l+1) pull from their parents
+template <int P>
+__global__ void __launch_bounds__(128) l2l_level_kernel(TreeData t, int lchild)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < (1 << lchild)) l2l_node<P>(t, kd_beg(lchild) + i);
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) l2l_top_kernel(TreeData t, int lfirst, int llast)
+{
+	for (int l = lfirst; l <= llast; ++l)
+	{
+		for (int i = threadIdx.x; i < (1 << l); i += blockDim.x)
+			l2l_node<P>(t, kd_beg(l) + i);
+		__syncthreads();
+	}
+}
+
+// L2P + rescale + optional elastic term + optional un-sort, one pass over the particles
+template <int P>
+__global__ void __launch_bounds__(128)
+l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__ acc_near, float *__restrict__ acc_out,
+           const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L)
+{
+	const float scale = param ? param[0] : 1.f;
+	float k3[3] = {1.f, 1.f, 1.f};
+	if (fuse_elastic && param) { k3[0] = param[3]; k3[1] = param[4]; k3[2] = param[5]; }
+	const int beg = kd_beg(L);
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+	{
+		// leaf of sorted position j: floor(2^L j / n) (:162-164)
+		const int leaf = (int)((((unsigned long long)j) << L) / (unsigned long long)n);
+		const float4 c = t.center[beg + leaf];
+		float Lq[trl_off(P + 1)], S[sym_off(P + 1)];
+		const float *src = t.local + (int64_t)(beg + leaf) * t.sL;
+#pragma unroll
+		for (int k = 0; k < trl_off(P + 1); ++k) Lq[k] = src[k];
+		S[0] = 0.f;
+		local_expand<P>(S, Lq);
+		const float x = spos[3*j], y = spos[3*j+1], z = spos[3*j+2];
+		float f[3];
+		l2p_field<P>(f, S, x - c.x, y - c.y, z - c.z);
+		float ax = (acc_near[3*j] + f[0]) * scale, ay = (acc_near[3*j+1] + f[1]) * scale, az = (acc_near[3*j+2] + f[2]) * scale;
+		if (fuse_elastic) { ax = fmaf(-k3[0], x, ax); ay = fmaf(-k3[1], y, ay); az = fmaf(-k3[2], z, az); }
+		const int64_t o = perm_or_null ? (int64_t)perm_or_null[j] : j;
+		acc_out[3*o] = ax; acc_out[3*o+1] = ay; acc_out[3*o+2] = az;
+	}
+}
+
+
+constexpr int kTopLevels = 7; // levels 0..7 of the upward / 2..8 of the downward pass run in one CTA
+
+template <int P>
+struct OrderImpl
+{
+	static void upward(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L)
+	{
+		cudaStream_t st = ctx->stream;
+		leaf_p2m_kernel<P><<<grid_for(1ll << L, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L); ++ctx->launches;
+		for (int l = L - 1; l > kTopLevels; --l)
+		{
+			m2m_level_kernel<P><<<((1 << l) + 127) / 128, 128, 0, st>>>(t, n, l); ++ctx->launches;
+		}
+		m2m_top_kernel<P><<<1, 256, 0, st>>>(t, n, std::min(L - 1, kTopLevels)); ++ctx->launches;
+	}
+	static void m2l(nbco_ctx *ctx, TreeData t, const int2 *list, const unsigned *count, unsigned cap, float eps2)
+	{
+		m2l_kernel<P><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2); ++ctx->launches;
+	}
+	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
+	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L)
+	{
+		cudaStream_t st = ctx->stream;
+		// locals of levels 0 and 1 stay zero (nothing is ever admissible there); level l+1 pulls from level l >= 1
+		if (L >= 2)
+		{
+			l2l_top_kernel<P><<<1, 256, 0, st>>>(t, 2, std::min(L, kTopLevels + 1)); ++ctx->launches;
+			for (int l = kTopLevels + 2; l <= L; ++l)
+			{
+				l2l_level_kernel<P><<<((1 << l) + 127) / 128, 128, 0, st>>>(t, l); ++ctx->launches;
+			}
+		}
+		l2p_kernel<P><<<grid_for(n, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
+		                                                                    param, fuse_elastic, n, L);
+		++ctx->launches;
+	}
+};
+
+} // namespace
+
+#define NBCO_INSTANTIATE_ORDER(P)                                                                          \
+	extern const OrderOps kOrderOps##P;                                                                    \
+	const OrderOps kOrderOps##P = {OrderImpl<P>::upward, OrderImpl<P>::m2l, OrderImpl<P>::downward};
+
+} // namespace nbco

@@ -1,0 +1,3 @@
+// order-2 instantiation of the FMM operator passes (see fmm3_order.cuh)
+#include "fmm3_order.cuh"
+namespace nbco { NBCO_INSTANTIATE_ORDER(2) }

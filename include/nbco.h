@@ -64,7 +64,7 @@ typedef struct nbco_config
 	int32_t world;         /* compute only this rank's shard of targets (see nbco_shard_range)      */
 } nbco_config;
 
-#define NBCO_MAX_ORDER 8
+#define NBCO_MAX_ORDER 6
 
 void nbco_default_config(nbco_config *cfg);
 int  nbco_abi_version(void);

@@ -766,3 +766,20 @@ void orc_get_lists(const orc_ctx *c, int *p2p, int *m2l)
 	if (p2p) { memcpy(p2p, c->p2p, sizeof(pair_t) * (size_t)c->p2p_n); qsort(p2p, (size_t)c->p2p_n, sizeof(pair_t), pair_cmp); }
 	if (m2l) { memcpy(m2l, c->m2l, sizeof(pair_t) * (size_t)c->m2l_n); qsort(m2l, (size_t)c->m2l_n, sizeof(pair_t), pair_cmp); }
 }
+
+/* ---------------- operator-level entry points (unit tests of the CUDA templates) ---------------- */
+void orc_op_p2m(float *M, int p, const float *d) { for (int q = 2; q <= p - 1; ++q) p2m_acc(M + sym_off(q), q, d); }
+void orc_op_m2m(float *Mout, const float *Min, int p, const float *d) { for (int q = 2; q <= p - 1; ++q) m2m_acc(Mout + sym_off(q), Min, q, d); }
+void orc_op_m2l(float *L, const float *M, int p, const float *d_unit, float r) { m2l_acc(L, M, p, d_unit, r); }
+void orc_op_l2l(float *Lchild, const float *Lparent, int p, const float *d)
+{
+	float S[(ORC_MAX_ORDER + 1) * (ORC_MAX_ORDER + 2) * (ORC_MAX_ORDER + 3) / 6];
+	local_expand(S, Lparent, p);
+	l2l_acc(Lchild, S, p, d);
+}
+void orc_op_l2p(float *f, const float *L, int p, const float *d)
+{
+	float S[(ORC_MAX_ORDER + 1) * (ORC_MAX_ORDER + 2) * (ORC_MAX_ORDER + 3) / 6];
+	local_expand(S, L, p);
+	l2p_field(f, S, p, d);
+}
