@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): 3D kd-tree FMM particle-steps/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n N] [--order P]
+
+A "step" = one leapfrog step of coulombOscillatorFMMKD3 (kick, drift, FMM + elastic force, kick)
+over all N particles, tree rebuilt every tree_steps = 8 force evaluations like the reference GPU
+path.  One JSON line is printed by rank 0 (see the task contract for the keys).  Inputs are the
+reference's own Gaussian initial conditions (initGA, fixed seed) generated on the host.
+
+  value      particle-steps/s with the state resident in HBM (nbco_integrate on device pointers)
+  e2e        the same metric through the host-buffer C-ABI call nbco_step_host: every step copies
+             [pos|vel|acc] host->device from pinned memory, runs one step, copies it back
+  roofline   dominant phase of the step against measured HBM bandwidth (algorithmic bytes from
+             SURVEY.md section 8(d), evaluated with the actual list sizes)
+  cpu_baseline  the UNMODIFIED reference CPU path (oracle/_ref, kind "reference") or, when that
+             library is absent, our C restatement (kind "port"), timed on the host cores
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= t <= t1 + 0.05:
+                    sm.append(float(f[0]))
+                    for nme, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nme)
+            except ValueError:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def fmm_bytes_per_eval(n, order, L, p2p_pairs, m2l_pairs):
+    """algorithmic bytes of one FMM evaluation per phase"""
+    Nl, Nn = 1 << L, (1 << (L + 1)) - 1
+    SM = 4 * order * (order + 1) * (order + 2) // 6
+    SL = 4 * (order + 1) ** 2
+    return {
+        "p2m_m2m": 12 * n + Nl * (12 + SM) + (2 * Nn - Nl) * (16 + SM),
+        "traverse": 40 * Nn + 8 * (m2l_pairs + p2p_pairs),
+        "m2l": 8 * m2l_pairs + Nn * (12 + SM) + Nn * SL,
+        "p2p": 8 * p2p_pairs + 8 * Nl + 24 * n,
+        "l2l_l2p": Nn * (12 + 2 * SL) + Nl * (12 + SL) + 36 * n,
+        "kd_build": (16 * L + 52) * n,
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import coulomb_oscillators_b200 as nb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    n, order = args.n, args.order
+    peaks, peak_kind = measured_peaks()
+
+    # Multi-GPU (N > 1): the FMM evaluator is not sharded yet (DESIGN.md "multi-GPU"): every rank
+    # steps an independent replica of the same system ("replicas only", weak scaling).
+    state = nb.init_ga(n)
+    par = nb.default_param(n)
+    ctx = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first)
+    buf = torch.empty(9 * n, dtype=torch.float32, device="cuda")
+    buf[:6 * n] = torch.from_numpy(state.reshape(-1)).cuda()
+    dpar = torch.from_numpy(par).cuda()
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    ev = nb.EVAL_COULOMB_FMM3_KD
+    dt = 5e-4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx.compute_force(ev, buf.data_ptr(), n, dpar.data_ptr())       # main3.cu:835-839
+    ctx.integrate(nb.LEAPFROG, ev, buf.data_ptr(), n, dpar.data_ptr(), dt, args.warmup)
+    ctx.fmm_phase_totals(reset=True)
+    l0 = ctx.fmm_info().kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record(stream)
+    ctx.integrate(nb.LEAPFROG, ev, buf.data_ptr(), n, dpar.data_ptr(), dt, args.steps)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    info = ctx.fmm_info()
+    launches = info.kernel_launches - l0
+    totals, evals, rebuilds = ctx.fmm_phase_totals(reset=True)
+    assert np.isfinite(buf[:6 * n].sum().item()), "state diverged"
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region, every step ----
+    hbuf = torch.empty(9 * n, dtype=torch.float32).pin_memory()
+    hbuf.copy_(buf.cpu())
+    hnp = hbuf.numpy()
+    ctx_e = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first)
+    e2e_steps = max(3, min(args.steps, 8))
+    ctx_e.step_host(nb.LEAPFROG, ev, hnp, n, par, dt, 1)   # warm-up (allocations, first rebuild)
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx_e.step_host(nb.LEAPFROG, ev, hnp, n, par, dt, 1)
+    torch.cuda.synchronize()
+    te = time.perf_counter() - te0
+    if world > 1:
+        t = torch.tensor([te], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+    e2e_value = world * n * e2e_steps / te
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * n * args.steps / (ms * 1e-3)
+    # ---- roofline of the dominant phase ----
+    bytes_eval = fmm_bytes_per_eval(n, order, info.levels, info.p2p_pairs, info.m2l_pairs)
+    phases = {}
+    for k, tot in totals.items():
+        calls = rebuilds if k == "kd_build" else evals
+        if calls == 0:
+            continue
+        avg_ms = tot / calls
+        phases[k] = {"avg_ms": round(avg_ms, 4), "share": round(tot / max(sum(totals.values()), 1e-9), 4),
+                     "GBps": round(bytes_eval[k] / (avg_ms * 1e-3) / 1e9, 1) if avg_ms > 0 else None}
+    dom = max(totals, key=lambda k: totals[k])
+    dcalls = rebuilds if dom == "kd_build" else evals
+    achieved = bytes_eval[dom] / (totals[dom] / dcalls * 1e-3) / 1e9
+    step_bytes = sum(v for k, v in bytes_eval.items() if k != "kd_build") + bytes_eval["kd_build"] / 8 + 60 * n
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None, "peak_kind": peak_kind,
+                "step_bytes_per_particle": round(step_bytes / n, 1),
+                "step_hbm_frac": round(step_bytes * (args.steps / (ms * 1e-3)) / 1e9 / peaks["hbm_gbs"], 4)}
+
+    cpu = cpu_baseline(n, order, args.m2l_first, bounded=True)
+    out = {
+        "metric": "3D FMM particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"3D kd-tree FMM leapfrog, N={n}, p={order}, r=1, tree_steps=8, reference initGA ICs"
+                               + (f", {world} independent replicas (FMM not sharded yet)" if world > 1 else ""),
+                   "n": n, "order": order, "levels": int(info.levels), "p2p_pairs": int(info.p2p_pairs),
+                   "m2l_pairs": int(info.m2l_pairs), "m2l_first": args.m2l_first,
+                   "l2_hygiene": "inputs larger than L2 (state 36 B x N + tree slab)" if 36 * n > 126e6 else "working set may fit L2",
+                   "e2e_copies": "every step: H2D [pos|vel|acc] from pinned memory + D2H of the same"},
+        "roofline": roofline, "phases": phases, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 36 * n, "d2h_bytes_per_step": 36 * n,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if args.direct:
+        out["direct_sum"] = bench_direct(nb, torch, local, peaks)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_direct(nb, torch, local, peaks, n=1 << 20):
+    """secondary metric of BASELINE.json: O(N^2) direct sum, FP32-FMA roofline (18 flop / interaction)"""
+    state = nb.init_ga(n)
+    pos = torch.from_numpy(state[0].copy()).cuda()
+    acc = torch.empty_like(pos)
+    par = torch.from_numpy(nb.default_param(n)).cuda()
+    ctx = nb.Context(device=local)
+    st = torch.cuda.ExternalStream(ctx.stream)
+    ctx.force_direct3(pos.data_ptr(), acc.data_ptr(), n, par.data_ptr())
+    best = 1e30
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        ctx.force_direct3(pos.data_ptr(), acc.data_ptr(), n, par.data_ptr())
+        e1.record(st)
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    inter = n * n / (best * 1e-3)
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    peak = 2 * sms * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    return {"n": n, "ms": best, "Ginteractions_per_s": inter / 1e9,
+            "roofline": {"bound": "fp32_fma", "achieved": inter * 18 / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": inter * 18 / 1e12 / peak, "flop_per_interaction": 18}}
+
+
+def cpu_baseline(n, order, m2l_first, bounded, steps=None, warmup=0):
+    """reference CPU path (oracle/_ref) timed on the host cores; bounded sample of the workload"""
+    from refs import Ref, Oracle
+    import coulomb_oscillators_b200 as nb
+    cores = os.cpu_count() or 1
+    if Ref.available():
+        ns = min(n, 1 << 21) if bounded else min(n, 1 << 22)
+        threads = min(cores, 64)
+        ref = Ref(order=order, threads=threads, unsort=0)
+        buf = np.zeros(9 * ns, np.float32)
+        buf[:6 * ns] = nb.init_ga(ns).reshape(-1)
+        par = nb.default_param(ns)
+        ref.eval(3, buf, ns, par)                       # precompute accelerations (main3.cu:835-839)
+        for _ in range(warmup):
+            ref.integrate(1, 3, buf, ns, par, 5e-4, 1)
+        k = steps or 3
+        t0 = time.perf_counter()
+        ref.integrate(1, 3, buf, ns, par, 5e-4, k)
+        t = time.perf_counter() - t0
+        return {"value": ns * k / t, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
+                "sample": f"{k} leapfrog steps of coulombOscillatorFMMKD3_cpu at N={ns} (p={order}, CPU_THREADS={threads}, "
+                          f"state already in tree order), {t:.1f} s", "ms_per_step": 1e3 * t / k}
+    ns = min(n, 1 << 18)
+    orc = Oracle(order=order, unsort=0, m2l_first=m2l_first, tree_steps=1)
+    buf = np.zeros(9 * ns, np.float32)
+    buf[:6 * ns] = nb.init_ga(ns).reshape(-1)
+    par = nb.default_param(ns)
+    orc.eval(3, buf, ns, par)
+    k = steps or 3
+    t0 = time.perf_counter()
+    orc.integrate(1, 3, buf, ns, par, 5e-4, k)
+    t = time.perf_counter() - t0
+    return {"value": ns * k / t, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{k} leapfrog steps of the C restatement at N={ns}, {t:.1f} s", "ms_per_step": 1e3 * t / k}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cpu = cpu_baseline(args.n, args.order, args.m2l_first, bounded=False, steps=args.steps, warmup=args.warmup)
+    out = {
+        "impl": "reference", "metric": "3D FMM particle-steps/s", "value": cpu["value"], "unit": "particle-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"3D kd-tree FMM leapfrog, N={args.n}, p={args.order}, r=1, reference initGA ICs "
+                               f"(reference CPU path timed on a bounded sample, see cpu_baseline.sample)",
+                   "n": args.n, "order": args.order},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1 << 24)
+    ap.add_argument("--order", type=int, default=3)
+    ap.add_argument("--m2l-first", dest="m2l_first", type=int, default=1)
+    ap.add_argument("--no-direct", dest="direct", action="store_false")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

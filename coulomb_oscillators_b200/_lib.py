@@ -33,8 +33,8 @@ SYMBOLS = [
     "nbco_default_config", "nbco_abi_version", "nbco_last_error", "nbco_create", "nbco_destroy",
     "nbco_set_config", "nbco_get_config", "nbco_stream", "nbco_force_direct3", "nbco_force_fmm3_kd",
     "nbco_coulomb_direct3", "nbco_coulomb_fmm3_kd", "nbco_add_elastic", "nbco_step", "nbco_compute_force",
-    "nbco_integrate", "nbco_mean_rel_err", "nbco_energy", "nbco_eval_host", "nbco_run_host",
-    "nbco_fmm_get_info", "nbco_fmm_get_tree", "nbco_fmm_get_lists", "nbco_fmm_get_phase_ms",
+    "nbco_integrate", "nbco_mean_rel_err", "nbco_energy", "nbco_eval_host", "nbco_run_host", "nbco_step_host",
+    "nbco_fmm_get_info", "nbco_fmm_get_tree", "nbco_fmm_get_lists", "nbco_fmm_get_phase_ms", "nbco_fmm_phase_totals",
     "nbco_shard_range", "nbco_init_ga", "nbco_init_test_cube", "nbco_state_read", "nbco_state_write", "nbco_free",
 ]
 
@@ -65,10 +65,12 @@ def _load():
     L.nbco_energy.argtypes = [vp, vp, i64, vp, C.POINTER(f64)]
     L.nbco_eval_host.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp]
     L.nbco_run_host.argtypes = [vp, C.c_int, C.c_int, vp, vp, i64, vp, f64, i64]
+    L.nbco_step_host.argtypes = [vp, C.c_int, C.c_int, vp, i64, vp, f64, i64]
     L.nbco_fmm_get_info.argtypes = [vp, C.POINTER(FmmInfo)]
     L.nbco_fmm_get_tree.argtypes = [vp] + [vp] * 9
     L.nbco_fmm_get_lists.argtypes = [vp, vp, i64, vp, i64]
     L.nbco_fmm_get_phase_ms.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(f32), C.c_int]
+    L.nbco_fmm_phase_totals.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(f64), C.c_int, C.POINTER(i64), C.c_int]
     L.nbco_shard_range.argtypes = [i64, C.c_int32, C.c_int32, C.POINTER(i64), C.POINTER(i64)]
     L.nbco_shard_range.restype = None
     L.nbco_init_ga.argtypes = [vp, i64, vp, vp]
@@ -211,6 +213,10 @@ class Context:
         _check(lib.nbco_run_host(self._h, scheme, evaluator, _hp(pos_vel), _hp(acc), n, _hp(param), dt, nsteps))
         return acc
 
+    def step_host(self, scheme, evaluator, buf, n, param, dt, nsteps=1):
+        """buf: flat float32 [pos|vel|acc] (9n), updated in place"""
+        _check(lib.nbco_step_host(self._h, scheme, evaluator, _hp(buf), n, _hp(param), dt, nsteps))
+
     # ---- FMM introspection ----
     def fmm_info(self):
         info = FmmInfo()
@@ -235,6 +241,14 @@ class Context:
         m2l = np.empty((i.m2l_pairs, 2), np.int32)
         _check(lib.nbco_fmm_get_lists(self._h, _hp(p2p), i.p2p_pairs, _hp(m2l), i.m2l_pairs))
         return p2p, m2l
+
+    def fmm_phase_totals(self, reset=False):
+        """({phase: total ms}, evaluations, rebuilds) since the last reset"""
+        names = (C.c_char_p * 32)()
+        ms = (C.c_double * 32)()
+        ev = (C.c_int64 * 2)()
+        k = lib.nbco_fmm_phase_totals(self._h, names, ms, 32, ev, 1 if reset else 0)
+        return {names[j].decode(): ms[j] for j in range(k)}, ev[0], ev[1]
 
     def fmm_phase_ms(self):
         names = (C.c_char_p * 32)()

@@ -347,6 +347,22 @@ int nbco_run_host(nbco_ctx *ctx, int scheme, int evaluator, float *h_pos_vel, fl
 	return sync(ctx);
 }
 
+int nbco_step_host(nbco_ctx *ctx, int scheme, int evaluator, float *h_buf, int64_t n,
+                   const float *h_param, double dt, int64_t nsteps)
+{
+	ENTER(ctx);
+	if (!h_buf || n <= 0) { set_error("bad host buffers"); return NBCO_ERR_INVALID; }
+	float *d_buf, *d_param;
+	NBCO_TRY(stage(ctx, n, h_param, &d_buf, &d_param));
+	const size_t vb = sizeof(float) * 3 * (size_t)n;
+	NBCO_CUDA(cudaMemcpyAsync(d_buf, h_buf, 3 * vb, cudaMemcpyHostToDevice, ctx->stream));
+	const float dtf = (float)dt;
+	for (int64_t s = 0; s < nsteps; ++s)
+		NBCO_TRY(scheme_step(ctx, scheme, evaluator, d_buf, n, d_param, dtf));
+	NBCO_CUDA(cudaMemcpyAsync(h_buf, d_buf, 3 * vb, cudaMemcpyDeviceToHost, ctx->stream));
+	return sync(ctx);
+}
+
 void nbco_shard_range(int64_t n, int32_t rank, int32_t world, int64_t *begin, int64_t *end)
 {
 	// ceil(n*i/w), the split rule of evalBox (fmm_cart3_kdtree.cuh:117-118)

@@ -607,6 +607,8 @@ struct FmmPlan
 	DevBuf p2p, m2l, frontA, frontB, cnt, bbox, mfac;
 	cudaEvent_t ev[PH_COUNT + 1];
 	bool ev_ok = false, ev_valid = false;
+	double tot_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	int64_t tot_evals = 0, tot_rebuilds = 0;
 	bool bottom_attr = false;
 };
 
@@ -827,6 +829,12 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 		NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
 		p.ev_valid = true;
 		p.rebuilt = rebuild;
+		for (int k = 0; k < PH_COUNT; ++k)
+		{
+			float ms = 0.f;
+			if (cudaEventElapsedTime(&ms, p.ev[k], p.ev[k + 1]) == cudaSuccess) p.tot_ms[k] += ms;
+		}
+		++p.tot_evals; p.tot_rebuilds += do_build ? 1 : 0;
 		p.p2p_n = h[0]; p.m2l_n = h[1];
 		if (h[0] <= p.cap_list && h[1] <= p.cap_list && h[5] == 0)
 		{
@@ -964,6 +972,17 @@ int nbco_fmm_get_phase_ms(nbco_ctx *ctx, const char **names, float *ms, int cap)
 		ms[k] = 0.f;
 		cudaEventElapsedTime(&ms[k], p.ev[k], p.ev[k + 1]);
 	}
+	return k;
+}
+
+int nbco_fmm_phase_totals(nbco_ctx *ctx, const char **names, double *ms, int cap, int64_t *h_evals, int reset)
+{
+	if (!ctx || !ctx->fmm) return 0;
+	FmmPlan &p = *ctx->fmm;
+	int k = 0;
+	for (; k < PH_COUNT && k < cap; ++k) { names[k] = kPhaseNames[k]; ms[k] = p.tot_ms[k]; }
+	if (h_evals) { h_evals[0] = p.tot_evals; h_evals[1] = p.tot_rebuilds; }
+	if (reset) { for (int i = 0; i < 8; ++i) p.tot_ms[i] = 0; p.tot_evals = p.tot_rebuilds = 0; }
 	return k;
 }
 

@@ -129,6 +129,12 @@ int nbco_eval_host(nbco_ctx *ctx, int evaluator, float *h_pos, float *h_vel, flo
 int nbco_run_host(nbco_ctx *ctx, int scheme, int evaluator, float *h_pos_vel, float *h_acc, int64_t n,
                   const float *h_param, double dt, int64_t nsteps);
 
+/* nsteps steps from a host state buffer [pos|vel|acc] (9n floats, acc valid on entry, e.g. from a
+ * previous call): H2D of all three arrays, nsteps steps of the scheme, D2H of all three.  With
+ * nsteps = 1 this is the end-to-end cost of one step when the state lives on the host. */
+int nbco_step_host(nbco_ctx *ctx, int scheme, int evaluator, float *h_buf, int64_t n,
+                   const float *h_param, double dt, int64_t nsteps);
+
 /* ---- introspection of the last FMM evaluation (parity tests, profiling) ---- */
 typedef struct nbco_fmm_info
 {
@@ -159,6 +165,10 @@ int nbco_fmm_get_lists(nbco_ctx *ctx, int32_t *h_p2p_pairs, int64_t p2p_cap,
 /* Per-phase device times (ms) of the last FMM evaluation, measured with CUDA events on the
  * context stream: names[i] points to a static string. Returns the number of phases. */
 int nbco_fmm_get_phase_ms(nbco_ctx *ctx, const char **names, float *ms, int cap);
+/* The same per phase, summed over all FMM evaluations since the last reset (ms), with the
+ * number of evaluations and how many of them rebuilt the tree in h_evals[0], h_evals[1].
+ * reset != 0 clears the sums after reading.  Returns the number of phases. */
+int nbco_fmm_phase_totals(nbco_ctx *ctx, const char **names, double *ms, int cap, int64_t *h_evals, int reset);
 
 /* ---- multi-GPU helpers ---- */
 /* Target shard [begin, end) of rank r of w over n items: the kd-tree's own equal split

@@ -1,0 +1,96 @@
+"""GPU parity of the direct sum (nbco_force_direct3) through the C ABI against the oracle,
+the golden fixture produced by the reference, and -- when present -- the reference itself."""
+import os
+
+import numpy as np
+import pytest
+
+import coulomb_oscillators_b200 as nb
+from refs import Oracle, Ref, mean_rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_MEAN, TOL_MAX = 1e-6, 1e-5   # north star: <= 1e-5 relative, fp32
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return nb.Context()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 129, 1000, 1025, 4097])
+def test_direct_matches_oracle_ragged_sizes(ctx, n):
+    rng = np.random.default_rng(n)
+    pos = (rng.normal(size=(n, 3)) * [0.003, 0.001, 0.01]).astype(np.float32)
+    par = nb.default_param(n)
+    a = ctx.eval_host(nb.EVAL_DIRECT3, pos.copy(), None, par)
+    o = Oracle().direct3(pos.copy(), par)
+    m, mx = mean_rel_err(a, o)
+    assert m < TOL_MEAN and mx < TOL_MAX
+
+
+def test_direct_matches_reference_fixture(ctx):
+    g = np.load(os.path.join(GOLD, "fmm_ga_n3000_p3.npz"))
+    a = ctx.eval_host(nb.EVAL_DIRECT3, g["pos"].copy(), None, g["param"])
+    m, mx = mean_rel_err(a, g["acc_direct"])
+    assert m < TOL_MEAN and mx < TOL_MAX
+
+
+def test_direct_unscaled_and_elastic(ctx):
+    n = 2000
+    st = nb.init_ga(n)
+    par = nb.default_param(n)
+    a0 = ctx.eval_host(nb.EVAL_DIRECT3, st[0].copy(), None, None)       # param == NULL: unscaled
+    a1 = ctx.eval_host(nb.EVAL_DIRECT3, st[0].copy(), None, par)
+    assert np.allclose(a1, a0 * par[0], rtol=1e-6, atol=0)
+    a2 = ctx.eval_host(nb.EVAL_COULOMB_DIRECT3, st[0].copy(), None, par)  # + elastic term (main3.cu:47-51)
+    want = a1 - st[0] * par[3:6]
+    assert np.allclose(a2, want, rtol=2e-6, atol=1e-12)
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not shipped")
+def test_direct_matches_live_reference_config1_size(ctx):
+    """BASELINE config 1 size (N = 8192) against direct3_cpu of the unmodified reference"""
+    n = 8192
+    st = nb.init_ga(n)
+    par = nb.default_param(n)
+    buf = np.zeros(9 * n, np.float32)
+    buf[:3 * n] = st[0].ravel()
+    Ref(threads=os.cpu_count()).eval(0, buf, n, par)
+    a = ctx.eval_host(nb.EVAL_DIRECT3, st[0].copy(), None, par)
+    m, mx = mean_rel_err(a, buf[6 * n:].reshape(n, 3))
+    assert m < TOL_MEAN and mx < TOL_MAX
+
+
+def test_direct_target_shards_tile_the_full_result():
+    """multi-GPU path on one device: rank r of w writes only its target shard; shards agree with world = 1"""
+    import torch
+    n = 5003
+    st = nb.init_ga(n)
+    pos = torch.from_numpy(st[0].copy()).cuda()
+    par = torch.from_numpy(nb.default_param(n)).cuda()
+    full = torch.empty_like(pos)
+    nb.Context().force_direct3(pos.data_ptr(), full.data_ptr(), n, par.data_ptr())
+    w = 4
+    out = torch.full_like(pos, float("nan"))
+    for r in range(w):
+        c = nb.Context(rank=r, world=w)
+        tmp = torch.full_like(pos, float("nan"))
+        c.force_direct3(pos.data_ptr(), tmp.data_ptr(), n, par.data_ptr())
+        b, e = nb.shard_range(n, r, w)
+        assert torch.isnan(tmp[:b]).all() and torch.isnan(tmp[e:]).all()
+        out[b:e] = tmp[b:e]
+    assert torch.equal(out, full)
+
+
+def test_direct_large_property_newton_third_law(ctx):
+    """full-size property (no oracle at this size): the total force of the pair term vanishes"""
+    import torch
+    n = 1 << 18
+    st = nb.init_ga(n)
+    pos = torch.from_numpy(st[0].copy()).cuda()
+    acc = torch.empty_like(pos)
+    ctx.force_direct3(pos.data_ptr(), acc.data_ptr(), n, None)
+    tot = acc.double().sum(0).abs().max().item()
+    scale = acc.double().abs().sum(0).max().item()
+    assert tot < 1e-6 * scale
