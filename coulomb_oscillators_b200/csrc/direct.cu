@@ -312,10 +312,10 @@ int direct3_launch(nbco_ctx *ctx, const float *d_pos, float *d_acc, int64_t n, c
 	{
 		case 1: LAUNCH(direct3_scalar_kernel, 2); break;
 		case 2: LAUNCH(direct3_scalar_kernel, 8); break;
-		case 3: LAUNCH(direct3_packed_kernel, 4); break;
+		case 3: LAUNCH(direct3_scalar_kernel, 4); break;
 		case 4: LAUNCH(direct3_packed_kernel, 8); break;
 		case 5: LAUNCH(direct3_packed_kernel, 2); break;
-		default: LAUNCH(direct3_scalar_kernel, 4); break;
+		default: LAUNCH(direct3_packed_kernel, 4); break; // measured fastest on B200 (profiles/)
 	}
 #undef LAUNCH
 	++ctx->launches;

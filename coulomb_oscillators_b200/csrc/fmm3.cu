@@ -90,18 +90,30 @@ __global__ void __launch_bounds__(256) evalbox_top_kernel(TreeGeom g, const u32 
 	write_box(g, node, lb, rb, g.chain[parent]);
 }
 
-struct TileRange { int64_t a, b; int seg; };
+struct TileRange { int64_t a, b; int seg, t; };
 
 __device__ __forceinline__ TileRange tile_range(int64_t n, int l, int tps)
 {
 	TileRange r;
 	r.seg = blockIdx.x / tps;
-	int t = blockIdx.x % tps;
+	r.t = blockIdx.x % tps;
 	int64_t s0 = seg_start(n, r.seg, l), s1 = seg_start(n, r.seg + 1, l);
-	r.a = s0 + (int64_t)t * kTile;
+	r.a = s0 + (int64_t)r.t * kTile;
 	r.b = r.a + kTile < s1 ? r.a + kTile : s1;
 	return r;
 }
+
+__device__ __forceinline__ void hist_add(u32 *sh, u32 digit, bool valid)
+// one shared atomic per distinct digit per warp (keys of a segment share their high bytes)
+{
+	u32 dg = valid ? digit : 0xffffffffu;
+	u32 peers = __match_any_sync(0xffffffffu, dg);
+	if (valid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[digit], (u32)__popc(peers));
+}
+
+// hist is stored [segment][digit][tile]: a plain exclusive scan of the flat array then yields the
+// destination offset of every (segment, digit, tile) bucket directly
+__device__ __forceinline__ int64_t hist_slot(int seg, int digit, int t, int tps) { return ((int64_t)seg * 256 + digit) * tps + t; }
 
 // keys of level l (evalKeys_kdtree, :158-192) fused with the digit-0 histogram
 __global__ void __launch_bounds__(256)
@@ -113,16 +125,22 @@ keygen_hist_kernel(const float *__restrict__ pos, const int *__restrict__ splitd
 	__syncthreads();
 	TileRange r = tile_range(n, l, tps);
 	const int axis = splitdim[kd_beg(l) + r.seg];
-	for (int64_t j = r.a + threadIdx.x; j < r.b; j += 256)
+	for (int64_t j0 = r.a; j0 < r.b; j0 += 256)
 	{
-		u32 id = idx_in ? idx_in[j] : (u32)j;
-		u32 key = ordered_bits(pos[3 * (int64_t)id + axis]);
-		keys[j] = key;
-		if (!idx_in) idx_out[j] = id;
-		atomicAdd(&sh[key & 255u], 1u);
+		const int64_t j = j0 + threadIdx.x;
+		const bool valid = j < r.b;
+		u32 key = 0;
+		if (valid)
+		{
+			u32 id = idx_in ? idx_in[j] : (u32)j;
+			key = ordered_bits(pos[3 * (int64_t)id + axis]);
+			keys[j] = key;
+			if (!idx_in) idx_out[j] = id;
+		}
+		hist_add(sh, key & 255u, valid);
 	}
 	__syncthreads();
-	hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
+	hist[hist_slot(r.seg, threadIdx.x, r.t, tps)] = sh[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(256)
@@ -132,35 +150,91 @@ hist_kernel(const u32 *__restrict__ keys, u32 *__restrict__ hist, int64_t n, int
 	sh[threadIdx.x] = 0;
 	__syncthreads();
 	TileRange r = tile_range(n, l, tps);
-	for (int64_t j = r.a + threadIdx.x; j < r.b; j += 256)
-		atomicAdd(&sh[(keys[j] >> shift) & 255u], 1u);
+	for (int64_t j0 = r.a; j0 < r.b; j0 += 256)
+	{
+		const int64_t j = j0 + threadIdx.x;
+		const bool valid = j < r.b;
+		hist_add(sh, valid ? ((keys[j] >> shift) & 255u) : 0u, valid);
+	}
 	__syncthreads();
-	hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
+	hist[hist_slot(r.seg, threadIdx.x, r.t, tps)] = sh[threadIdx.x];
 }
 
-// per segment: counts -> destination offsets, ordered (digit, tile); in place
-__global__ void __launch_bounds__(256) seg_scan_kernel(u32 *__restrict__ hist, int64_t n, int l, int tps)
+// device-wide exclusive scan of the flat histogram (three small kernels: block sums, spine, apply)
+constexpr int kScanPer = 8, kScanBlock = 256, kScanChunk = kScanPer * kScanBlock;
+
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *sh, u32 &total)
+// exclusive scan of one value per thread over a 256-thread block
 {
-	__shared__ u32 sh[256];
-	const int seg = blockIdx.x, d = threadIdx.x;
-	u32 *h = hist + (int64_t)seg * tps * 256;
-	u32 total = 0;
-	for (int t = 0; t < tps; ++t) total += h[t * 256 + d];
-	sh[d] = total;
-	__syncthreads();
-	for (int o = 1; o < 256; o <<= 1) // inclusive Hillis-Steele scan over the 256 digits
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	u32 incl = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
 	{
-		u32 v = (d >= o) ? sh[d - o] : 0;
-		__syncthreads();
-		sh[d] += v;
-		__syncthreads();
+		u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += x;
 	}
-	u32 run = (u32)seg_start(n, seg, l) + sh[d] - total;
-	for (int t = 0; t < tps; ++t)
+	if (lane == 31) sh[w] = incl;
+	__syncthreads();
+	if (w == 0)
 	{
-		u32 c = h[t * 256 + d];
-		h[t * 256 + d] = run;
-		run += c;
+		u32 ws = lane < (kScanBlock / 32) ? sh[lane] : 0, wi = ws;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			u32 x = __shfl_up_sync(0xffffffffu, wi, o);
+			if (lane >= o) wi += x;
+		}
+		if (lane < (kScanBlock / 32)) sh[lane] = wi - ws;
+		if (lane == 31) sh[32] = wi;
+	}
+	__syncthreads();
+	total = sh[32];
+	u32 r = sh[w] + incl - v;
+	__syncthreads();
+	return r;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(const u32 *__restrict__ h, u32 *__restrict__ bsum, int64_t m)
+{
+	__shared__ u32 sh[33];
+	const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanPer;
+	u32 v = 0;
+#pragma unroll
+	for (int k = 0; k < kScanPer; ++k) if (base + k < m) v += h[base + k];
+	u32 total;
+	block_exclusive_scan(v, sh, total);
+	if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_spine_kernel(u32 *__restrict__ bsum, int nb)
+{
+	__shared__ u32 sh[33];
+	u32 carry = 0;
+	for (int b0 = 0; b0 < nb; b0 += kScanBlock)
+	{
+		const int i = b0 + threadIdx.x;
+		u32 v = i < nb ? bsum[i] : 0, total;
+		u32 ex = block_exclusive_scan(v, sh, total);
+		if (i < nb) bsum[i] = carry + ex;
+		carry += total;
+	}
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(u32 *__restrict__ h, const u32 *__restrict__ bsum, int64_t m)
+{
+	__shared__ u32 sh[33];
+	const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanPer;
+	u32 x[kScanPer], v = 0;
+#pragma unroll
+	for (int k = 0; k < kScanPer; ++k) { x[k] = base + k < m ? h[base + k] : 0; v += x[k]; }
+	u32 total;
+	u32 run = bsum[blockIdx.x] + block_exclusive_scan(v, sh, total);
+#pragma unroll
+	for (int k = 0; k < kScanPer; ++k)
+	{
+		if (base + k < m) h[base + k] = run;
+		run += x[k];
 	}
 }
 
@@ -194,7 +268,7 @@ scatter_kernel(const u32 *__restrict__ kin, const u32 *__restrict__ iin, u32 *__
 	__syncthreads();
 	{
 		const int d = threadIdx.x;
-		u32 run = offs[(int64_t)blockIdx.x * 256 + d];
+		u32 run = offs[hist_slot(r.seg, d, r.t, tps)];
 #pragma unroll
 		for (int ww = 0; ww < kWarps; ++ww) { u32 c = wcnt[ww][d]; wcnt[ww][d] = run; run += c; }
 	}
@@ -603,7 +677,7 @@ struct FmmPlan
 	int64_t p2p_n = 0, m2l_n = 0;
 	u32 cap_list = 0, cap_front = 0;
 	DevBuf lbound, rbound, size2, splitdim, chain, center, mpole, local;
-	DevBuf keysA, keysB, idxA, idxB, hist, spos, perm, tmp3, accn;
+	DevBuf keysA, keysB, idxA, idxB, hist, bsum, spos, perm, tmp3, accn;
 	DevBuf p2p, m2l, frontA, frontB, cnt, bbox, mfac;
 	cudaEvent_t ev[PH_COUNT + 1];
 	bool ev_ok = false, ev_valid = false;
@@ -657,6 +731,7 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	NBCO_TRY(p.tmp3.reserve(12 * (size_t)n)); NBCO_TRY(p.accn.reserve(12 * (size_t)n));
 	const size_t tiles = (size_t)((n + kTile - 1) / kTile) + (1u << std::min(lt, L)) + 1;
 	NBCO_TRY(p.hist.reserve(4 * 256 * tiles));
+	NBCO_TRY(p.bsum.reserve(4 * (256 * tiles / kScanChunk + 2)));
 	if (p.cap_list < (u32)std::min<int64_t>(8ll * p.ntot + 1024, 0x7fffffff))
 	{
 		p.cap_list = (u32)std::min<int64_t>(8ll * p.ntot + 1024, 0x7fffffff);
@@ -694,6 +769,7 @@ static int build_tree(nbco_ctx *ctx, FmmPlan &p, const float *pos)
 
 	u32 *kA = p.keysA.as<u32>(), *kB = p.keysB.as<u32>(), *iA = p.idxA.as<u32>(), *iB = p.idxB.as<u32>();
 	u32 *hist = p.hist.as<u32>();
+	u32 *bsum = p.bsum.as<u32>();
 	const int ltop = std::min(p.lt, p.L); // levels [0, ltop) are sorted globally
 	for (int l = 0; l < ltop; ++l)
 	{
@@ -708,7 +784,14 @@ static int build_tree(nbco_ctx *ctx, FmmPlan &p, const float *pos)
 			u32 *kin = (pass & 1) ? kB : kA, *iin = (pass & 1) ? iB : iA;
 			u32 *kout = (pass & 1) ? kA : kB, *iout = (pass & 1) ? iA : iB;
 			if (pass > 0) { hist_kernel<<<tiles, 256, 0, st>>>(kin, hist, n, l, tps, 8 * pass); LAUNCHED(ctx); }
-			seg_scan_kernel<<<nseg, 256, 0, st>>>(hist, n, l, tps); LAUNCHED(ctx);
+			{
+				const int64_t m = (int64_t)tiles * 256;
+				const int nb = (int)((m + kScanChunk - 1) / kScanChunk);
+				scan_reduce_kernel<<<nb, kScanBlock, 0, st>>>(hist, bsum, m);
+				scan_spine_kernel<<<1, kScanBlock, 0, st>>>(bsum, nb);
+				scan_apply_kernel<<<nb, kScanBlock, 0, st>>>(hist, bsum, m);
+				ctx->launches += 3;
+			}
 			scatter_kernel<<<tiles, 256, 0, st>>>(kin, iin, kout, iout, hist, n, l, tps, 8 * pass); LAUNCHED(ctx);
 		}
 	}
@@ -874,7 +957,7 @@ void fmm3_destroy(nbco_ctx *ctx)
 	if (!ctx->fmm) return;
 	FmmPlan &p = *ctx->fmm;
 	DevBuf *all[] = {&p.lbound, &p.rbound, &p.size2, &p.splitdim, &p.chain, &p.center, &p.mpole, &p.local,
-	                 &p.keysA, &p.keysB, &p.idxA, &p.idxB, &p.hist, &p.spos, &p.perm, &p.tmp3, &p.accn,
+	                 &p.keysA, &p.keysB, &p.idxA, &p.idxB, &p.hist, &p.bsum, &p.spos, &p.perm, &p.tmp3, &p.accn,
 	                 &p.p2p, &p.m2l, &p.frontA, &p.frontB, &p.cnt, &p.bbox, &p.mfac};
 	for (DevBuf *b : all) b->release();
 	if (p.ev_ok) for (int i = 0; i <= PH_COUNT; ++i) cudaEventDestroy(p.ev[i]);

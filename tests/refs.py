@@ -195,3 +195,17 @@ class Ref:
         t["p2p"] = canon(p2p, counts[0])
         t["m2l"] = canon(m2l, counts[1])
         return t
+
+
+def unique_axes(pos):
+    """make every coordinate of every axis distinct (bump duplicates by one ulp until strictly
+    increasing): on such inputs the reference's unstable sorts have a unique answer"""
+    pos = np.array(pos, np.float32, copy=True)
+    for k in range(3):
+        o = np.argsort(pos[:, k], kind="stable")
+        v = pos[o, k].copy()
+        for i in range(1, len(v)):
+            if v[i] <= v[i - 1]:
+                v[i] = np.nextafter(v[i - 1], np.float32(np.inf))
+        pos[o, k] = v
+    return pos

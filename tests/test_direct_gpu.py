@@ -45,7 +45,7 @@ def test_direct_unscaled_and_elastic(ctx):
     assert np.allclose(a1, a0 * par[0], rtol=1e-6, atol=0)
     a2 = ctx.eval_host(nb.EVAL_COULOMB_DIRECT3, st[0].copy(), None, par)  # + elastic term (main3.cu:47-51)
     want = a1 - st[0] * par[3:6]
-    assert np.allclose(a2, want, rtol=2e-6, atol=1e-12)
+    assert np.abs(a2 - want).max() <= 1e-6 * np.abs(want).max()   # fma(-k, x, a) vs a - k*x: one rounding apart
 
 
 @pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not shipped")

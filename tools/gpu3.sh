@@ -1,0 +1,3 @@
+python -m pytest tests -q -m gpu 2>&1 | tail -25
+python tools/fmm_check.py 16777216 3 1 2>&1 | head -6
+python tools/fmm_check.py 1048576 3 1 2>&1 | head -6
