@@ -118,11 +118,13 @@ def run_ours(args):
     n, order = args.n, args.order
     peaks, peak_kind = measured_peaks()
 
-    # Multi-GPU (N > 1): the FMM evaluator is not sharded yet (DESIGN.md "multi-GPU"): every rank
-    # steps an independent replica of the same system ("replicas only", weak scaling).
+    # Multi-GPU (N > 1): ONE system of n particles, strong scaling.  The kd-tree is replicated, rank r of
+    # 2^g computes the subtree of node (g, r): its P2P / M2L / L2L / L2P and kick/drift; one NCCL
+    # all-gather of the drifted positions per step (parallel.fmm_leapfrog_sharded).
+    from coulomb_oscillators_b200.parallel import fmm_leapfrog_sharded
     state = nb.init_ga(n)
     par = nb.default_param(n)
-    ctx = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first)
+    ctx = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first, rank=rank, world=world)
     buf = torch.empty(9 * n, dtype=torch.float32, device="cuda")
     buf[:6 * n] = torch.from_numpy(state.reshape(-1)).cuda()
     dpar = torch.from_numpy(par).cuda()
@@ -136,8 +138,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(k):
+        if world == 1:
+            ctx.integrate(nb.LEAPFROG, ev, buf.data_ptr(), n, dpar.data_ptr(), dt, k)
+        else:
+            fmm_leapfrog_sharded(ctx, buf, n, dpar.data_ptr(), dt, k)
+
     ctx.compute_force(ev, buf.data_ptr(), n, dpar.data_ptr())       # main3.cu:835-839
-    ctx.integrate(nb.LEAPFROG, ev, buf.data_ptr(), n, dpar.data_ptr(), dt, args.warmup)
+    run_steps(args.warmup)
     ctx.fmm_phase_totals(reset=True)
     l0 = ctx.fmm_info().kernel_launches
     sampler = ClockSampler(local)
@@ -148,7 +156,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record(stream)
-    ctx.integrate(nb.LEAPFROG, ev, buf.data_ptr(), n, dpar.data_ptr(), dt, args.steps)
+    run_steps(args.steps)
     e1.record(stream)
     e1.synchronize()
     barrier()
@@ -168,27 +176,38 @@ def run_ours(args):
     hbuf = torch.empty(9 * n, dtype=torch.float32).pin_memory()
     hbuf.copy_(buf.cpu())
     hnp = hbuf.numpy()
-    ctx_e = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first)
+    ctx_e = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first, rank=rank, world=world)
     e2e_steps = max(3, min(args.steps, 8))
-    ctx_e.step_host(nb.LEAPFROG, ev, hnp, n, par, dt, 1)   # warm-up (allocations, first rebuild)
+
+    def e2e_step():
+        if world == 1:
+            ctx_e.step_host(nb.LEAPFROG, ev, hnp, n, par, dt, 1)
+        else:  # every rank uploads the state, the ranks step it together, every rank reads it back
+            buf.copy_(hbuf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            fmm_leapfrog_sharded(ctx_e, buf, n, dpar.data_ptr(), dt, 1)
+            hbuf.copy_(buf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    e2e_step()   # warm-up (allocations, first rebuild)
     barrier()
     te0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx_e.step_host(nb.LEAPFROG, ev, hnp, n, par, dt, 1)
+        e2e_step()
     torch.cuda.synchronize()
     te = time.perf_counter() - te0
     if world > 1:
         t = torch.tensor([te], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te = float(t.item())
-    e2e_value = world * n * e2e_steps / te
+    e2e_value = n * e2e_steps / te
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    value = world * n * args.steps / (ms * 1e-3)
+    value = n * args.steps / (ms * 1e-3)   # one system of n particles, whatever the number of GPUs
     # ---- roofline of the dominant phase ----
     bytes_eval = fmm_bytes_per_eval(n, order, info.levels, info.p2p_pairs, info.m2l_pairs)
     phases = {}
@@ -208,13 +227,14 @@ def run_ours(args):
                 "step_bytes_per_particle": round(step_bytes / n, 1),
                 "step_hbm_frac": round(step_bytes * (args.steps / (ms * 1e-3)) / 1e9 / peaks["hbm_gbs"], 4)}
 
-    cpu = cpu_baseline(n, order, args.m2l_first, bounded=True)
+    cpu = cpu_baseline(n, order, args.m2l_first, bounded=True) if world == 1 else None
     out = {
         "metric": "3D FMM particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"3D kd-tree FMM leapfrog, N={n}, p={order}, r=1, tree_steps=8, reference initGA ICs"
-                               + (f", {world} independent replicas (FMM not sharded yet)" if world > 1 else ""),
+                               + (f", sharded over {world} GPUs (replicated tree, per-rank subtree evaluation, "
+                                  f"all-gather of positions per step)" if world > 1 else ""),
                    "n": n, "order": order, "levels": int(info.levels), "p2p_pairs": int(info.p2p_pairs),
                    "m2l_pairs": int(info.m2l_pairs), "m2l_first": args.m2l_first,
                    "l2_hygiene": "inputs larger than L2 (state 36 B x N + tree slab)" if 36 * n > 126e6 else "working set may fit L2",
@@ -224,7 +244,7 @@ def run_ours(args):
                 "steps": e2e_steps},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    if args.direct:
+    if args.direct and world == 1:
         out["direct_sum"] = bench_direct(nb, torch, local, peaks)
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -25,7 +25,8 @@ class Config(C.Structure):
 class FmmInfo(C.Structure):
     _fields_ = [("levels", C.c_int32), ("order", C.c_int32), ("n", C.c_int64), ("nodes", C.c_int64),
                 ("p2p_pairs", C.c_int64), ("m2l_pairs", C.c_int64), ("off_m", C.c_int32), ("off_l", C.c_int32),
-                ("rebuilt", C.c_int32), ("mlt_max", C.c_int32), ("kernel_launches", C.c_int64)]
+                ("rebuilt", C.c_int32), ("mlt_max", C.c_int32), ("kernel_launches", C.c_int64),
+                ("counter", C.c_int32), ("reserved", C.c_int32)]
 
 
 # every symbol include/nbco.h declares (tests/test_abi.py checks this list against the header)

@@ -31,437 +31,6 @@ namespace nbco {
 namespace {
 
 // =====================================================================================
-//  bounding box (replaces minmaxReduce2, reductions.cuh:67-80: two CUB passes -> one pass)
-// =====================================================================================
-__global__ void __launch_bounds__(256) bbox_kernel(const float *__restrict__ pos, int64_t n, u32 *__restrict__ out6)
-{
-	float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-	{
-#pragma unroll
-		for (int k = 0; k < 3; ++k)
-		{
-			float v = pos[3*i+k];
-			mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v);
-		}
-	}
-#pragma unroll
-	for (int k = 0; k < 3; ++k)
-		for (int o = 16; o > 0; o >>= 1)
-		{
-			mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-			mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-		}
-	if ((threadIdx.x & 31) == 0)
-#pragma unroll
-		for (int k = 0; k < 3; ++k)
-		{
-			atomicMin(out6 + k, ordered_bits(mn[k]));
-			atomicMax(out6 + 3 + k, ordered_bits(mx[k]));
-		}
-}
-
-__global__ void root_box_kernel(TreeGeom g, const u32 *__restrict__ bb)
-{
-	if (threadIdx.x == 0 && blockIdx.x == 0)
-	{
-		float lb[3], rb[3];
-		for (int k = 0; k < 3; ++k) { lb[k] = unordered_bits(bb[k]); rb[k] = unordered_bits(bb[3+k]); }
-		write_box(g, 0, lb, rb, kNoAxis | (kNoAxis << 2) | (kNoAxis << 4));
-	}
-}
-
-// =====================================================================================
-//  top levels: segmented stable LSD radix sort of (key, id) pairs
-// =====================================================================================
-
-// boxes of level l from the sorted keys of level l-1 (evalBox_krnl, :109-137)
-__global__ void __launch_bounds__(256) evalbox_top_kernel(TreeGeom g, const u32 *__restrict__ keys, int64_t n, int l)
-{
-	int j = blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= (1 << l)) return;
-	int node = kd_beg(l) + j, parent = (node - 1) >> 1, split = g.splitdim[parent];
-	float lb[3], rb[3];
-	for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*parent+k]; rb[k] = g.rbound[3*parent+k]; }
-	int64_t s0 = seg_start(n, j, l), s1 = seg_start(n, j + 1, l);
-	if (node == 2*parent + 2) lb[split] = unordered_bits(keys[s0]);
-	else rb[split] = unordered_bits(keys[s1 - 1]);
-	write_box(g, node, lb, rb, g.chain[parent]);
-}
-
-struct TileRange { int64_t a, b; int seg, t; };
-
-__device__ __forceinline__ TileRange tile_range(int64_t n, int l, int tps)
-{
-	TileRange r;
-	r.seg = blockIdx.x / tps;
-	r.t = blockIdx.x % tps;
-	int64_t s0 = seg_start(n, r.seg, l), s1 = seg_start(n, r.seg + 1, l);
-	r.a = s0 + (int64_t)r.t * kTile;
-	r.b = r.a + kTile < s1 ? r.a + kTile : s1;
-	return r;
-}
-
-__device__ __forceinline__ void hist_add(u32 *sh, u32 digit, bool valid)
-// one shared atomic per distinct digit per warp (keys of a segment share their high bytes)
-{
-	u32 dg = valid ? digit : 0xffffffffu;
-	u32 peers = __match_any_sync(0xffffffffu, dg);
-	if (valid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[digit], (u32)__popc(peers));
-}
-
-// hist is stored [segment][digit][tile]: a plain exclusive scan of the flat array then yields the
-// destination offset of every (segment, digit, tile) bucket directly
-__device__ __forceinline__ int64_t hist_slot(int seg, int digit, int t, int tps) { return ((int64_t)seg * 256 + digit) * tps + t; }
-
-// keys of level l (evalKeys_kdtree, :158-192) fused with the digit-0 histogram
-__global__ void __launch_bounds__(256)
-keygen_hist_kernel(const float *__restrict__ pos, const int *__restrict__ splitdim, const u32 *__restrict__ idx_in,
-                   u32 *__restrict__ keys, u32 *__restrict__ idx_out, u32 *__restrict__ hist, int64_t n, int l, int tps)
-{
-	__shared__ u32 sh[256];
-	sh[threadIdx.x] = 0;
-	__syncthreads();
-	TileRange r = tile_range(n, l, tps);
-	const int axis = splitdim[kd_beg(l) + r.seg];
-	for (int64_t j0 = r.a; j0 < r.b; j0 += 256)
-	{
-		const int64_t j = j0 + threadIdx.x;
-		const bool valid = j < r.b;
-		u32 key = 0;
-		if (valid)
-		{
-			u32 id = idx_in ? idx_in[j] : (u32)j;
-			key = ordered_bits(pos[3 * (int64_t)id + axis]);
-			keys[j] = key;
-			if (!idx_in) idx_out[j] = id;
-		}
-		hist_add(sh, key & 255u, valid);
-	}
-	__syncthreads();
-	hist[hist_slot(r.seg, threadIdx.x, r.t, tps)] = sh[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(256)
-hist_kernel(const u32 *__restrict__ keys, u32 *__restrict__ hist, int64_t n, int l, int tps, int shift)
-{
-	__shared__ u32 sh[256];
-	sh[threadIdx.x] = 0;
-	__syncthreads();
-	TileRange r = tile_range(n, l, tps);
-	for (int64_t j0 = r.a; j0 < r.b; j0 += 256)
-	{
-		const int64_t j = j0 + threadIdx.x;
-		const bool valid = j < r.b;
-		hist_add(sh, valid ? ((keys[j] >> shift) & 255u) : 0u, valid);
-	}
-	__syncthreads();
-	hist[hist_slot(r.seg, threadIdx.x, r.t, tps)] = sh[threadIdx.x];
-}
-
-// device-wide exclusive scan of the flat histogram (three small kernels: block sums, spine, apply)
-constexpr int kScanPer = 8, kScanBlock = 256, kScanChunk = kScanPer * kScanBlock;
-
-__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *sh, u32 &total)
-// exclusive scan of one value per thread over a 256-thread block
-{
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	u32 incl = v;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1)
-	{
-		u32 x = __shfl_up_sync(0xffffffffu, incl, o);
-		if (lane >= o) incl += x;
-	}
-	if (lane == 31) sh[w] = incl;
-	__syncthreads();
-	if (w == 0)
-	{
-		u32 ws = lane < (kScanBlock / 32) ? sh[lane] : 0, wi = ws;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
-		{
-			u32 x = __shfl_up_sync(0xffffffffu, wi, o);
-			if (lane >= o) wi += x;
-		}
-		if (lane < (kScanBlock / 32)) sh[lane] = wi - ws;
-		if (lane == 31) sh[32] = wi;
-	}
-	__syncthreads();
-	total = sh[32];
-	u32 r = sh[w] + incl - v;
-	__syncthreads();
-	return r;
-}
-
-__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(const u32 *__restrict__ h, u32 *__restrict__ bsum, int64_t m)
-{
-	__shared__ u32 sh[33];
-	const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanPer;
-	u32 v = 0;
-#pragma unroll
-	for (int k = 0; k < kScanPer; ++k) if (base + k < m) v += h[base + k];
-	u32 total;
-	block_exclusive_scan(v, sh, total);
-	if (threadIdx.x == 0) bsum[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(kScanBlock) scan_spine_kernel(u32 *__restrict__ bsum, int nb)
-{
-	__shared__ u32 sh[33];
-	u32 carry = 0;
-	for (int b0 = 0; b0 < nb; b0 += kScanBlock)
-	{
-		const int i = b0 + threadIdx.x;
-		u32 v = i < nb ? bsum[i] : 0, total;
-		u32 ex = block_exclusive_scan(v, sh, total);
-		if (i < nb) bsum[i] = carry + ex;
-		carry += total;
-	}
-}
-
-__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(u32 *__restrict__ h, const u32 *__restrict__ bsum, int64_t m)
-{
-	__shared__ u32 sh[33];
-	const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanPer;
-	u32 x[kScanPer], v = 0;
-#pragma unroll
-	for (int k = 0; k < kScanPer; ++k) { x[k] = base + k < m ? h[base + k] : 0; v += x[k]; }
-	u32 total;
-	u32 run = bsum[blockIdx.x] + block_exclusive_scan(v, sh, total);
-#pragma unroll
-	for (int k = 0; k < kScanPer; ++k)
-	{
-		if (base + k < m) h[base + k] = run;
-		run += x[k];
-	}
-}
-
-__global__ void __launch_bounds__(256)
-scatter_kernel(const u32 *__restrict__ kin, const u32 *__restrict__ iin, u32 *__restrict__ kout, u32 *__restrict__ iout,
-               const u32 *__restrict__ offs, int64_t n, int l, int tps, int shift)
-{
-	constexpr int kWarps = 8, kIters = kTile / (kWarps * 32);
-	__shared__ u32 wcnt[kWarps][256];
-	for (int i = threadIdx.x; i < kWarps * 256; i += 256) (&wcnt[0][0])[i] = 0;
-	__syncthreads();
-	TileRange r = tile_range(n, l, tps);
-	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const u32 lt_mask = (1u << lane) - 1u;
-	u32 key[kIters], id[kIters], rank[kIters];
-#pragma unroll
-	for (int it = 0; it < kIters; ++it)
-	{
-		int64_t j = r.a + (int64_t)w * (kTile / kWarps) + it * 32 + lane;
-		bool valid = j < r.b;
-		key[it] = valid ? kin[j] : 0u;
-		id[it] = valid ? iin[j] : 0u;
-		u32 dg = valid ? ((key[it] >> shift) & 255u) : (256u + lane);
-		u32 peers = __match_any_sync(0xffffffffu, dg);
-		u32 prior = valid ? wcnt[w][dg] : 0u;
-		rank[it] = prior + __popc(peers & lt_mask);
-		__syncwarp();
-		if (valid && lane == __ffs(peers) - 1) wcnt[w][dg] = prior + __popc(peers);
-		__syncwarp();
-	}
-	__syncthreads();
-	{
-		const int d = threadIdx.x;
-		u32 run = offs[hist_slot(r.seg, d, r.t, tps)];
-#pragma unroll
-		for (int ww = 0; ww < kWarps; ++ww) { u32 c = wcnt[ww][d]; wcnt[ww][d] = run; run += c; }
-	}
-	__syncthreads();
-#pragma unroll
-	for (int it = 0; it < kIters; ++it)
-	{
-		int64_t j = r.a + (int64_t)w * (kTile / kWarps) + it * 32 + lane;
-		if (j < r.b)
-		{
-			u32 dst = wcnt[w][(key[it] >> shift) & 255u] + rank[it];
-			kout[dst] = key[it];
-			iout[dst] = id[it];
-		}
-	}
-}
-
-// final order when every level was a top level: perm = id, spos = pos[id]
-__global__ void __launch_bounds__(256)
-gather_sorted_kernel(const float *__restrict__ pos, const u32 *__restrict__ idx, float *__restrict__ spos, int *__restrict__ perm, int64_t n)
-{
-	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
-	{
-		u32 id = idx[j];
-		perm[j] = (int)id;
-		spos[3*j] = pos[3*(int64_t)id]; spos[3*j+1] = pos[3*(int64_t)id+1]; spos[3*j+2] = pos[3*(int64_t)id+2];
-	}
-}
-
-// =====================================================================================
-//  bottom levels: one CTA per level-lt node, particles resident in shared memory
-// =====================================================================================
-struct BottomSmem
-{
-	float *sx, *sy, *sz;
-	u64 *comp;
-};
-
-__device__ __forceinline__ float slot_coord(const BottomSmem &s, int axis, u32 slot)
-{
-	return axis == 0 ? s.sx[slot] : (axis == 1 ? s.sy[slot] : s.sz[slot]);
-}
-
-// strict "a before b" in the order a stable sort on the split axis would produce
-__device__ __forceinline__ bool comp_less(u64 a, u64 b, const BottomSmem &s, int chain, const u32 *__restrict__ idx_in, int64_t s0)
-{
-	u64 ka = a >> 13, kb = b >> 13;
-	if (ka != kb) return ka < kb;
-	if (a == ~0ull) return false;
-	u32 sa = (u32)a & kSlotMask, sb = (u32)b & kSlotMask;
-	for (int c = 1; c < 3; ++c)
-	{
-		int ax = (chain >> (2 * c)) & 3;
-		if (ax == kNoAxis) break;
-		u32 ua = ordered_bits(slot_coord(s, ax, sa)), ub = ordered_bits(slot_coord(s, ax, sb));
-		if (ua != ub) return ua < ub;
-	}
-	u32 ia = idx_in ? idx_in[s0 + sa] : sa, ib = idx_in ? idx_in[s0 + sb] : sb;
-	return ia < ib;
-}
-
-__global__ void __launch_bounds__(kBottomThreads, 1)
-kd_bottom_kernel(TreeGeom g, const float *__restrict__ pos, const u32 *__restrict__ idx_in,
-                 float *__restrict__ spos, int *__restrict__ perm, int64_t n, int lt, int L, int P2)
-{
-	extern __shared__ unsigned char smem_raw[];
-	BottomSmem s;
-	s.comp = reinterpret_cast<u64 *>(smem_raw);
-	s.sx = reinterpret_cast<float *>(smem_raw + sizeof(u64) * kBottomCap);
-	s.sy = s.sx + kBottomCap;
-	s.sz = s.sy + kBottomCap;
-	const int tid = threadIdx.x;
-	const int b = blockIdx.x;
-	const int64_t s0 = seg_start(n, b, lt);
-	const int c0 = (int)(seg_start(n, b + 1, lt) - s0);
-
-	for (int t = tid; t < c0; t += kBottomThreads)
-	{
-		int64_t id = idx_in ? (int64_t)idx_in[s0 + t] : s0 + t;
-		s.sx[t] = pos[3*id]; s.sy[t] = pos[3*id+1]; s.sz[t] = pos[3*id+2];
-	}
-	__syncthreads();
-
-	const int nlev = L - lt; // sorting levels lt .. L-1
-	for (int j = 0; j < nlev; ++j)
-	{
-		const int l = lt + j;
-		const int B = P2 >> j, logB = 31 - __clz(B);
-		// (a) composite words (key << 13 | slot) of every block, padded with ~0
-		for (int p = tid; p < P2; p += kBottomThreads)
-		{
-			int q = p >> logB, t = p & (B - 1);
-			int64_t i = ((int64_t)b << j) + q;
-			int cnt = (int)(seg_start(n, i + 1, l) - seg_start(n, i, l));
-			u64 c = ~0ull;
-			if (t < cnt)
-			{
-				u32 slot = (j == 0) ? (u32)t : ((u32)s.comp[p] & kSlotMask);
-				int axis = g.splitdim[kd_beg(l) + (int)i];
-				c = ((u64)ordered_bits(slot_coord(s, axis, slot)) << 13) | slot;
-			}
-			s.comp[p] = c;
-		}
-		__syncthreads();
-		// (b) bitonic sort inside every block of B words
-		for (int k = 2; k <= B; k <<= 1)
-			for (int jj = k >> 1; jj > 0; jj >>= 1)
-			{
-				for (int t = tid; t < (P2 >> 1); t += kBottomThreads)
-				{
-					int lo = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
-					int hi = lo | jj;
-					bool asc = (lo & k) == 0 || k == B;
-					// inside a block the final merge (k == B) is ascending for every block
-					u64 a = s.comp[lo], c = s.comp[hi];
-					int chain = 0;
-					bool tie = (a >> 13) == (c >> 13) && a != ~0ull;
-					if (tie) chain = g.chain[kd_beg(l) + (int)(((int64_t)b << j) + (lo >> logB))];
-					bool sw = asc ? comp_less(c, a, s, chain, idx_in, s0) : comp_less(a, c, s, chain, idx_in, s0);
-					if (sw) { s.comp[lo] = c; s.comp[hi] = a; }
-				}
-				__syncthreads();
-			}
-		// (c) boxes of the children (evalBox_krnl for level l+1)
-		for (int q = tid; q < (1 << j); q += kBottomThreads)
-		{
-			int64_t i = ((int64_t)b << j) + q;
-			int node = kd_beg(l) + (int)i;
-			int kl = (int)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
-			int axis = g.splitdim[node], pch = g.chain[node];
-			float lb[3], rb[3];
-			for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
-			float cl = slot_coord(s, axis, (u32)s.comp[q * B + kl - 1] & kSlotMask);
-			float cr = slot_coord(s, axis, (u32)s.comp[q * B + kl] & kSlotMask);
-			float save = rb[axis];
-			rb[axis] = cl;
-			write_box(g, 2*node + 1, lb, rb, pch);
-			rb[axis] = save; lb[axis] = cr;
-			write_box(g, 2*node + 2, lb, rb, pch);
-		}
-		if (j + 1 < nlev)
-		{
-			// (d) move every right child to the start of the second half of its parent's block
-			constexpr int kPer = kBottomCap / kBottomThreads;
-			u64 v[kPer];
-			const int Bh = B >> 1, logBh = logB - 1;
-#pragma unroll
-			for (int e = 0; e < kPer; ++e)
-			{
-				int p = tid + e * kBottomThreads;
-				v[e] = ~0ull;
-				if (p < P2)
-				{
-					int q2 = p >> logBh, t = p & (Bh - 1), q = q2 >> 1;
-					int64_t i2 = ((int64_t)b << (j + 1)) + q2;
-					int cnt = (int)(seg_start(n, i2 + 1, l + 1) - seg_start(n, i2, l + 1));
-					int kl = (int)(seg_start(n, (i2 | 1), l + 1) - seg_start(n, (i2 & ~1ll), l + 1));
-					if (t < cnt) v[e] = s.comp[q * B + ((q2 & 1) ? kl + t : t)];
-				}
-			}
-			__syncthreads();
-#pragma unroll
-			for (int e = 0; e < kPer; ++e)
-			{
-				int p = tid + e * kBottomThreads;
-				if (p < P2) s.comp[p] = v[e];
-			}
-		}
-		__syncthreads();
-	}
-	// output: storage order = order after the level-(L-1) sort
-	{
-		const int j = nlev - 1, l = L - 1;
-		const int B = P2 >> j, logB = 31 - __clz(B);
-		for (int p = tid; p < P2; p += kBottomThreads)
-		{
-			int q = p >> logB, t = p & (B - 1);
-			int64_t i = ((int64_t)b << j) + q;
-			int64_t st = seg_start(n, i, l);
-			int cnt = (int)(seg_start(n, i + 1, l) - st);
-			if (t < cnt)
-			{
-				u32 slot = (u32)s.comp[p] & kSlotMask;
-				int64_t dst = st + t;
-				perm[dst] = idx_in ? (int)idx_in[s0 + slot] : (int)(s0 + slot);
-				spos[3*dst] = s.sx[slot]; spos[3*dst+1] = s.sy[slot]; spos[3*dst+2] = s.sz[slot];
-			}
-		}
-	}
-}
-
-// =====================================================================================
 //  permutation glue (replaces the gather_krnl/copy_krnl pairs, kernel.cuh:228-311)
 // =====================================================================================
 __global__ void __launch_bounds__(256) gather3_kernel(const float *__restrict__ src, const int *__restrict__ perm, float *__restrict__ dst, int64_t n)
@@ -488,6 +57,7 @@ struct TravArgs
 	int64_t n;
 	int ntot, L, m2l_first;
 	float radius;
+	int64_t sh_lo, sh_hi; // particles (tree order) whose accelerations this rank computes
 };
 
 __device__ __forceinline__ int node_mult(int64_t n, int node, int &level)
@@ -495,6 +65,14 @@ __device__ __forceinline__ int node_mult(int64_t n, int node, int &level)
 	level = node_level(node);
 	int i = node - kd_beg(level);
 	return (int)(seg_start(n, i + 1, level) - seg_start(n, i, level));
+}
+
+// multi-GPU: a node is a target of this rank iff its particle range meets the rank's shard
+__device__ __forceinline__ bool node_mine(const TravArgs &a, int node)
+{
+	const int level = node_level(node);
+	const int i = node - kd_beg(level);
+	return seg_start(a.n, i, level) < a.sh_hi && seg_start(a.n, i + 1, level) > a.sh_lo;
 }
 
 // kd_admissible (:401-414) with the host's operation order; pow() comes from the host table
@@ -551,10 +129,16 @@ __global__ void __launch_bounds__(256) traverse_round_kernel(TravArgs a, int rou
 			else if (xl || (!yl && a.size2[np.x] <= a.size2[np.y])) kind = 4;
 			else kind = 5;
 		}
+		// bit 0: np.x is a target of this rank, bit 1: np.y is; untouched pairs (and their
+		// descendants) are dropped.  With one rank every node is a target (flags = 3).
+		int flags = 0;
+		if (kind) flags = (node_mine(a, np.x) ? 1 : 0) | (node_mine(a, np.y) ? 2 : 0);
+		if (!flags) kind = 0;
+		const int2 tagged = make_int2(np.x | (flags << kFlagShift), np.y);
 		u32 s1 = warp_append(a.cnt + 0, kind == 1);
-		if (kind == 1 && s1 < a.cap_p2p) a.p2p[s1] = np;
+		if (kind == 1 && s1 < a.cap_p2p) a.p2p[s1] = tagged;
 		u32 s2 = warp_append(a.cnt + 1, kind == 2);
-		if (kind == 2 && s2 < a.cap_m2l) a.m2l[s2] = np;
+		if (kind == 2 && s2 < a.cap_m2l) a.m2l[s2] = tagged;
 		int nf = kind == 3 ? 3 : (kind >= 4 ? 2 : 0);
 		u32 s3 = warp_append(cout, nf);
 		if (nf && s3 + nf > a.cap_front) a.cnt[5] = 1u; // sticky: a frontier did not fit
@@ -603,25 +187,26 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 template <int G, bool SELF>
 __global__ void __launch_bounds__(256)
 p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap, const float *__restrict__ spos,
-           float *__restrict__ acc, int64_t n, int L, float eps2)
+           float *__restrict__ acc, int64_t n, int L, float eps2, int leaf_lo, int leaf_hi)
 {
 	const int lane = threadIdx.x & (G - 1);
 	const int groups = (gridDim.x * blockDim.x) / G;
 	const int beg = kd_beg(L);
-	const u32 npairs = SELF ? (1u << L) : min(*count, cap);
+	const u32 npairs = SELF ? (u32)(leaf_hi - leaf_lo) : min(*count, cap);
 	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
 	const u32 nwork = ((npairs + (32 / G) - 1) / (32 / G)) * (32 / G); // keep whole warps in the loop
 	for (u32 w = (blockIdx.x * blockDim.x + threadIdx.x) / G; w < nwork; w += groups)
 	{
 		if (w >= npairs) continue;
-		int l1, l2;
-		if (SELF) { l1 = l2 = (int)w; }
-		else { int2 np = list[w]; l1 = np.x - beg; l2 = np.y - beg; }
+		int l1, l2, flags = 3;
+		if (SELF) { l1 = l2 = leaf_lo + (int)w; }
+		else { int2 np = list[w]; flags = (np.x >> kFlagShift) & 3; l1 = (np.x & kNodeMask) - beg; l2 = np.y - beg; }
 		const int64_t i1 = seg_start(n, l1, L), i2 = seg_start(n, l2, L);
 		const int m1 = (int)(seg_start(n, l1 + 1, L) - i1), m2 = (int)(seg_start(n, l2 + 1, L) - i2);
 #pragma unroll 1
 		for (int dir = 0; dir < (SELF ? 1 : 2); ++dir)
 		{
+			if (!SELF && !((flags >> dir) & 1)) continue; // the other rank owns these targets
 			const int64_t ti = dir ? i2 : i1, si = dir ? i1 : i2;
 			const int tm = dir ? m2 : m1, sm = dir ? m1 : m2;
 			for (int h0 = 0; h0 < tm; h0 += G)
@@ -646,6 +231,7 @@ p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap
 						r2 = fmaf(dy, dy, r2);
 						r2 = fmaf(dz, dz, r2);
 						float wv = rsqrt_approx(r2);
+						wv = wv * fmaf(-0.5f * r2 * wv, wv, 1.5f); // one Newton step: error of the near field ~1e-7
 						float w3 = (wv * wv) * wv;
 						ax = fmaf(dx, w3, ax); ay = fmaf(dy, w3, ay); az = fmaf(dz, w3, az);
 					}
@@ -671,19 +257,18 @@ static const char *kPhaseNames[PH_COUNT] = {"kd_build", "p2m_m2m", "traverse", "
 struct FmmPlan
 {
 	int64_t n = 0;
-	int L = 0, lt = 0, ntot = 0, order = 0, offM = 0, offL = 0, sM = 0, sL = 0, mlt_max = 0;
+	int L = 0, ntot = 0, order = 0, offM = 0, offL = 0, sM = 0, sL = 0, mlt_max = 0;
 	int counter = 0, rebuilt = 0, max_level = -1;
 	float dens = 0.f;
 	int64_t p2p_n = 0, m2l_n = 0;
 	u32 cap_list = 0, cap_front = 0;
-	DevBuf lbound, rbound, size2, splitdim, chain, center, mpole, local;
-	DevBuf keysA, keysB, idxA, idxB, hist, bsum, spos, perm, tmp3, accn;
-	DevBuf p2p, m2l, frontA, frontB, cnt, bbox, mfac;
+	KdTree kd;
+	DevBuf center, mpole, local, tmp3, accn;
+	DevBuf p2p, m2l, frontA, frontB, cnt, mfac;
 	cudaEvent_t ev[PH_COUNT + 1];
 	bool ev_ok = false, ev_valid = false;
 	double tot_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	int64_t tot_evals = 0, tot_rebuilds = 0;
-	bool bottom_attr = false;
 };
 
 static int plan_levels(int64_t n, int order, float dens, int max_level)
@@ -717,21 +302,11 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	p.sM = (p.offM + 3) & ~3; p.sL = (p.offL + 3) & ~3;
 	p.mlt_max = (int)((n - 1) / (1ll << L) + 1);
 	p.counter = 0;
-	// first level whose segments fit a bottom CTA
-	int lt = 0;
-	while (((n - 1) >> lt) + 1 > kBottomCap) ++lt;
-	p.lt = lt;
 	const size_t nt = (size_t)p.ntot;
-	NBCO_TRY(p.lbound.reserve(12 * nt)); NBCO_TRY(p.rbound.reserve(12 * nt)); NBCO_TRY(p.size2.reserve(4 * nt));
-	NBCO_TRY(p.splitdim.reserve(4 * nt)); NBCO_TRY(p.chain.reserve(4 * nt)); NBCO_TRY(p.center.reserve(16 * nt));
+	NBCO_TRY(kd_reserve(ctx, p.kd, n, L));
+	NBCO_TRY(p.center.reserve(16 * nt));
 	NBCO_TRY(p.mpole.reserve(4 * nt * p.sM)); NBCO_TRY(p.local.reserve(4 * nt * p.sL));
-	NBCO_TRY(p.keysA.reserve(4 * (size_t)n)); NBCO_TRY(p.keysB.reserve(4 * (size_t)n));
-	NBCO_TRY(p.idxA.reserve(4 * (size_t)n)); NBCO_TRY(p.idxB.reserve(4 * (size_t)n));
-	NBCO_TRY(p.spos.reserve(12 * (size_t)n)); NBCO_TRY(p.perm.reserve(4 * (size_t)n));
 	NBCO_TRY(p.tmp3.reserve(12 * (size_t)n)); NBCO_TRY(p.accn.reserve(12 * (size_t)n));
-	const size_t tiles = (size_t)((n + kTile - 1) / kTile) + (1u << std::min(lt, L)) + 1;
-	NBCO_TRY(p.hist.reserve(4 * 256 * tiles));
-	NBCO_TRY(p.bsum.reserve(4 * (256 * tiles / kScanChunk + 2)));
 	if (p.cap_list < (u32)std::min<int64_t>(8ll * p.ntot + 1024, 0x7fffffff))
 	{
 		p.cap_list = (u32)std::min<int64_t>(8ll * p.ntot + 1024, 0x7fffffff);
@@ -739,7 +314,7 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	}
 	NBCO_TRY(p.p2p.reserve(8 * (size_t)p.cap_list)); NBCO_TRY(p.m2l.reserve(8 * (size_t)p.cap_list));
 	NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
-	NBCO_TRY(p.cnt.reserve(64)); NBCO_TRY(p.bbox.reserve(64)); NBCO_TRY(p.mfac.reserve(4 * 2 * 40));
+	NBCO_TRY(p.cnt.reserve(64)); NBCO_TRY(p.mfac.reserve(4 * 2 * 40));
 	// MAC factor table: M = pow(mult / N, 1/(3p+6)) evaluated with the host libm like the
 	// reference CPU path (:410); a node of level l holds floor(n/2^l) or floor(n/2^l)+1 particles
 	float tab[2 * 32];
@@ -756,72 +331,6 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 
 #define LAUNCHED(ctx) do { ++(ctx)->launches; } while (0)
 
-static int build_tree(nbco_ctx *ctx, FmmPlan &p, const float *pos)
-{
-	cudaStream_t st = ctx->stream;
-	const int64_t n = p.n;
-	TreeGeom g{p.lbound.as<float>(), p.rbound.as<float>(), p.size2.as<float>(), p.splitdim.as<int>(), p.chain.as<int>()};
-	u32 *bb = p.bbox.as<u32>();
-	static const u32 bb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-	NBCO_CUDA(cudaMemcpyAsync(bb, bb_init, sizeof(bb_init), cudaMemcpyHostToDevice, st));
-	bbox_kernel<<<grid_for(n, 256, ctx->sm_count, 4), 256, 0, st>>>(pos, n, bb); LAUNCHED(ctx);
-	root_box_kernel<<<1, 32, 0, st>>>(g, bb); LAUNCHED(ctx);
-
-	u32 *kA = p.keysA.as<u32>(), *kB = p.keysB.as<u32>(), *iA = p.idxA.as<u32>(), *iB = p.idxB.as<u32>();
-	u32 *hist = p.hist.as<u32>();
-	u32 *bsum = p.bsum.as<u32>();
-	const int ltop = std::min(p.lt, p.L); // levels [0, ltop) are sorted globally
-	for (int l = 0; l < ltop; ++l)
-	{
-		const int nseg = 1 << l;
-		const int64_t maxseg = ((n - 1) >> l) + 1;
-		const int tps = (int)((maxseg + kTile - 1) / kTile);
-		const int tiles = nseg * tps;
-		if (l > 0) { evalbox_top_kernel<<<(nseg + 255) / 256, 256, 0, st>>>(g, kA, n, l); LAUNCHED(ctx); }
-		keygen_hist_kernel<<<tiles, 256, 0, st>>>(pos, g.splitdim, l == 0 ? nullptr : iA, kA, iA, hist, n, l, tps); LAUNCHED(ctx);
-		for (int pass = 0; pass < 4; ++pass)
-		{
-			u32 *kin = (pass & 1) ? kB : kA, *iin = (pass & 1) ? iB : iA;
-			u32 *kout = (pass & 1) ? kA : kB, *iout = (pass & 1) ? iA : iB;
-			if (pass > 0) { hist_kernel<<<tiles, 256, 0, st>>>(kin, hist, n, l, tps, 8 * pass); LAUNCHED(ctx); }
-			{
-				const int64_t m = (int64_t)tiles * 256;
-				const int nb = (int)((m + kScanChunk - 1) / kScanChunk);
-				scan_reduce_kernel<<<nb, kScanBlock, 0, st>>>(hist, bsum, m);
-				scan_spine_kernel<<<1, kScanBlock, 0, st>>>(bsum, nb);
-				scan_apply_kernel<<<nb, kScanBlock, 0, st>>>(hist, bsum, m);
-				ctx->launches += 3;
-			}
-			scatter_kernel<<<tiles, 256, 0, st>>>(kin, iin, kout, iout, hist, n, l, tps, 8 * pass); LAUNCHED(ctx);
-		}
-	}
-	if (ltop > 0) { evalbox_top_kernel<<<((1 << ltop) + 255) / 256, 256, 0, st>>>(g, kA, n, ltop); LAUNCHED(ctx); }
-	if (ltop < p.L)
-	{
-		const size_t smem = (sizeof(u64) + 3 * sizeof(float)) * kBottomCap;
-		if (!p.bottom_attr)
-		{
-			NBCO_CUDA(cudaFuncSetAttribute(kd_bottom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-			p.bottom_attr = true;
-		}
-		int64_t maxseg = ((n - 1) >> ltop) + 1;
-		int P2 = 2; while (P2 < maxseg) P2 <<= 1;
-		// the sort needs at least 2 words per block down to the last level
-		while ((P2 >> (p.L - 1 - ltop)) < 2) P2 <<= 1;
-		if (P2 > kBottomCap) { set_error("internal: bottom block %d", P2); return NBCO_ERR_INVALID; }
-		kd_bottom_kernel<<<1 << ltop, kBottomThreads, smem, st>>>(g, pos, ltop == 0 ? nullptr : iA, p.spos.as<float>(),
-		                                                         p.perm.as<int>(), n, ltop, p.L, P2);
-		LAUNCHED(ctx);
-	}
-	else
-	{
-		gather_sorted_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(pos, iA, p.spos.as<float>(), p.perm.as<int>(), n);
-		LAUNCHED(ctx);
-	}
-	NBCO_CUDA(cudaGetLastError());
-	return NBCO_OK;
-}
-
 static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_pos, float *d_acc, const float *d_param, bool fuse_elastic, bool rebuild)
 {
 	cudaStream_t st = ctx->stream;
@@ -834,14 +343,14 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	const float *spos = d_pos; // tree-ordered positions the passes read
 	if (rebuild)
 	{
-		NBCO_TRY(build_tree(ctx, p, d_pos));
+		NBCO_TRY(kd_build(ctx, p.kd, d_pos));
 		if (c.unsort)
-			spos = p.spos.as<float>();
+			spos = p.kd.spos.as<float>();
 		else
 		{
 			// leave pos and the velocities behind it in tree order (:1359-1360,1758-1759)
-			NBCO_CUDA(cudaMemcpyAsync(d_pos, p.spos.p, 12 * (size_t)n, cudaMemcpyDeviceToDevice, st));
-			gather3_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(d_pos + 3*n, p.perm.as<int>(), p.tmp3.as<float>(), n); LAUNCHED(ctx);
+			NBCO_CUDA(cudaMemcpyAsync(d_pos, p.kd.spos.p, 12 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+			gather3_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(d_pos + 3*n, p.kd.perm.as<int>(), p.tmp3.as<float>(), n); LAUNCHED(ctx);
 			NBCO_CUDA(cudaMemcpyAsync(d_pos + 3*n, p.tmp3.p, 12 * (size_t)n, cudaMemcpyDeviceToDevice, st));
 		}
 	}
@@ -851,11 +360,16 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_TRAVERSE], st));
 	TravArgs a;
-	a.center = t.center; a.size2 = p.size2.as<float>(); a.mfac = p.mfac.as<float>();
+	a.center = t.center; a.size2 = p.kd.size2.as<float>(); a.mfac = p.mfac.as<float>();
 	a.p2p = p.p2p.as<int2>(); a.m2l = p.m2l.as<int2>();
 	a.cnt = p.cnt.as<u32>();
 	a.cap_p2p = a.cap_m2l = p.cap_list; a.cap_front = p.cap_front;
 	a.n = n; a.ntot = p.ntot; a.L = L; a.m2l_first = c.m2l_first; a.radius = c.radius;
+	// multi-GPU: rank r of 2^g owns the subtree of node (g, r): a contiguous range of leaves and particles
+	int g = 0;
+	while ((1 << g) < c.world) ++g;
+	const int leaf_lo = c.rank << (L - g), leaf_hi = (c.rank + 1) << (L - g);
+	a.sh_lo = seg_start(n, c.rank, g); a.sh_hi = seg_start(n, c.rank + 1, g);
 	traverse_init_kernel<<<1, 32, 0, st>>>(p.frontA.as<int2>(), a.cnt); LAUNCHED(ctx);
 	const int rounds = 2 * L + 2;
 	for (int r = 0; r < rounds; ++r)
@@ -873,8 +387,8 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 		const int blocks = ctx->sm_count * 8;
 #define P2P_LAUNCH(G)                                                                                              \
 		do {                                                                                                       \
-			p2p_kernel<G, false><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2);   \
-			p2p_kernel<G, true><<<blocks, 256, 0, st>>>(nullptr, nullptr, 0, spos, accn, n, L, c.eps2);            \
+			p2p_kernel<G, false><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2, leaf_lo, leaf_hi); \
+			p2p_kernel<G, true><<<blocks, 256, 0, st>>>(nullptr, nullptr, 0, spos, accn, n, L, c.eps2, leaf_lo, leaf_hi);        \
 		} while (0)
 		if (p.mlt_max <= 4) P2P_LAUNCH(4);
 		else if (p.mlt_max <= 8) P2P_LAUNCH(8);
@@ -888,7 +402,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	ops.m2l(ctx, t, a.m2l, a.cnt + 1, a.cap_m2l, c.eps2);
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_DOWNWARD], st));
-	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L);
+	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g);
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_COUNT], st));
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;
@@ -896,9 +410,16 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 
 int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const float *d_param, bool fuse_elastic)
 {
-	if (ctx->cfg.world != 1) { set_error("fmm3_kd: multi-GPU sharding is not available yet"); return NBCO_ERR_INVALID; }
+	if (ctx->cfg.world != 1)
+	{
+		// sharded evaluation: the tree is replicated, every rank computes the accelerations of its own subtree
+		if (ctx->cfg.world & (ctx->cfg.world - 1)) { set_error("fmm3_kd: world size must be a power of two"); return NBCO_ERR_INVALID; }
+		if (ctx->cfg.unsort) { set_error("fmm3_kd: sharded evaluation needs unsort = 0 (shards are ranges of the tree order)"); return NBCO_ERR_INVALID; }
+	}
 	NBCO_TRY(ensure_plan(ctx, n));
 	FmmPlan &p = *ctx->fmm;
+	if ((1 << p.L) < ctx->cfg.world) { set_error("fmm3_kd: more ranks than leaves"); return NBCO_ERR_INVALID; }
+	if (p.L > 26) { set_error("fmm3_kd: depth %d exceeds the list encoding", p.L); return NBCO_ERR_INVALID; }
 	const bool rebuild = ctx->cfg.unsort || (p.counter % ctx->cfg.tree_steps == 0);
 	bool do_build = rebuild;
 	for (int attempt = 0; attempt < 6; ++attempt)
@@ -956,9 +477,8 @@ void fmm3_destroy(nbco_ctx *ctx)
 {
 	if (!ctx->fmm) return;
 	FmmPlan &p = *ctx->fmm;
-	DevBuf *all[] = {&p.lbound, &p.rbound, &p.size2, &p.splitdim, &p.chain, &p.center, &p.mpole, &p.local,
-	                 &p.keysA, &p.keysB, &p.idxA, &p.idxB, &p.hist, &p.bsum, &p.spos, &p.perm, &p.tmp3, &p.accn,
-	                 &p.p2p, &p.m2l, &p.frontA, &p.frontB, &p.cnt, &p.bbox, &p.mfac};
+	kd_release(p.kd);
+	DevBuf *all[] = {&p.center, &p.mpole, &p.local, &p.tmp3, &p.accn, &p.p2p, &p.m2l, &p.frontA, &p.frontB, &p.cnt, &p.mfac};
 	for (DevBuf *b : all) b->release();
 	if (p.ev_ok) for (int i = 0; i <= PH_COUNT; ++i) cudaEventDestroy(p.ev[i]);
 	delete ctx->fmm;
@@ -978,6 +498,7 @@ int nbco_fmm_get_info(nbco_ctx *ctx, nbco_fmm_info *info)
 	info->levels = p.L; info->order = p.order; info->n = p.n; info->nodes = p.ntot;
 	info->p2p_pairs = p.p2p_n; info->m2l_pairs = p.m2l_n; info->off_m = p.offM; info->off_l = p.offL;
 	info->rebuilt = p.rebuilt; info->mlt_max = p.mlt_max; info->kernel_launches = ctx->launches;
+	info->counter = p.counter;
 	return NBCO_OK;
 }
 
@@ -989,10 +510,10 @@ int nbco_fmm_get_tree(nbco_ctx *ctx, float *h_center, float *h_lbound, float *h_
 	FmmPlan &p = *ctx->fmm;
 	const size_t nt = (size_t)p.ntot;
 	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
-	if (h_lbound) NBCO_CUDA(cudaMemcpy(h_lbound, p.lbound.p, 12 * nt, cudaMemcpyDeviceToHost));
-	if (h_rbound) NBCO_CUDA(cudaMemcpy(h_rbound, p.rbound.p, 12 * nt, cudaMemcpyDeviceToHost));
-	if (h_splitdim) NBCO_CUDA(cudaMemcpy(h_splitdim, p.splitdim.p, 4 * nt, cudaMemcpyDeviceToHost));
-	if (h_perm) NBCO_CUDA(cudaMemcpy(h_perm, p.perm.p, 4 * (size_t)p.n, cudaMemcpyDeviceToHost));
+	if (h_lbound) NBCO_CUDA(cudaMemcpy(h_lbound, p.kd.lbound.p, 12 * nt, cudaMemcpyDeviceToHost));
+	if (h_rbound) NBCO_CUDA(cudaMemcpy(h_rbound, p.kd.rbound.p, 12 * nt, cudaMemcpyDeviceToHost));
+	if (h_splitdim) NBCO_CUDA(cudaMemcpy(h_splitdim, p.kd.splitdim.p, 4 * nt, cudaMemcpyDeviceToHost));
+	if (h_perm) NBCO_CUDA(cudaMemcpy(h_perm, p.kd.perm.p, 4 * (size_t)p.n, cudaMemcpyDeviceToHost));
 	if (h_center)
 	{
 		std::vector<float> tmp(4 * nt);
@@ -1034,6 +555,7 @@ int nbco_fmm_get_lists(nbco_ctx *ctx, int32_t *h_p2p, int64_t p2p_cap, int32_t *
 		if (!dst || cnt == 0) return NBCO_OK;
 		NBCO_CUDA(cudaMemcpy(dst, src.p, 8 * (size_t)cnt, cudaMemcpyDeviceToHost));
 		int2 *q = reinterpret_cast<int2 *>(dst);
+		for (int64_t i = 0; i < cnt; ++i) q[i].x &= kNodeMask;
 		std::sort(q, q + cnt, [](const int2 &a, const int2 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
 		return NBCO_OK;
 	};

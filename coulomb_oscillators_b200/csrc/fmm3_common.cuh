@@ -9,12 +9,15 @@ namespace nbco {
 
 typedef unsigned long long u64;
 typedef unsigned int u32;
+typedef unsigned short u16;
 
 constexpr int kTile = 4096;        // elements per radix tile (256 threads x 16)
 constexpr int kBottomCap = 8192;   // particles a bottom CTA keeps in shared memory
 constexpr int kBottomThreads = 1024;
 constexpr u32 kSlotMask = 0x1FFFu; // 13 bits: slot inside a bottom CTA
 constexpr int kNoAxis = 3;
+constexpr int kFlagShift = 28;             // interaction-list entries carry two target flags above the node id
+constexpr int kNodeMask = (1 << kFlagShift) - 1;
 
 // ---- index arithmetic of the implicit tree (fmm_cart3_kdtree.cuh:33-78,117-118) ----
 __host__ __device__ __forceinline__ int kd_beg(int l) { return (1 << l) - 1; }
@@ -90,14 +93,28 @@ struct TreeData
 	int sM, sL;
 };
 
+// kd-tree geometry and build scratch (kdtree.cu)
+struct KdTree
+{
+	int64_t n = 0;
+	int L = 0, lt = 0;
+	DevBuf lbound, rbound, size2, splitdim, chain;   // per node
+	DevBuf keys, idxA, idxB, tie, hist, sel, cur, spos, perm, bbox;
+	bool bottom_attr = false;
+};
+int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L);
+int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos);
+void kd_release(KdTree &t);
+
 // Order-specific passes (one translation unit per order: the unrolled templates are expensive
 // to compile, the reference's single TU takes > 4 min).
 struct OrderOps
 {
 	void (*upward)(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L);
 	void (*m2l)(nbco_ctx *ctx, TreeData t, const int2 *list, const unsigned *count, unsigned cap, float eps2);
+	// rank r of 2^g ranks pushes locals down its own subtree (plus the ancestors of its root) only
 	void (*downward)(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                 const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L);
+	                 const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g);
 };
 const OrderOps *order_ops(int order);
 

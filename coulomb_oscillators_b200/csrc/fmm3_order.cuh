@@ -10,6 +10,37 @@ using namespace ops;
 
 namespace {
 
+// node tuples are padded to a multiple of 4 floats and 16-byte aligned: move them as float4
+template <int N> constexpr int pad4() { return (N + 3) & ~3; }
+
+template <int N>
+__device__ __forceinline__ void load_tuple(float *dst /* pad4<N>() */, const float *__restrict__ src)
+{
+#pragma unroll
+	for (int k = 0; k < pad4<N>() / 4; ++k)
+	{
+		const float4 v = reinterpret_cast<const float4 *>(src)[k];
+		dst[4*k] = v.x; dst[4*k+1] = v.y; dst[4*k+2] = v.z; dst[4*k+3] = v.w;
+	}
+}
+
+template <int N>
+__device__ __forceinline__ void store_tuple(float *__restrict__ dst, const float *src /* pad4<N>() */)
+{
+#pragma unroll
+	for (int k = 0; k < pad4<N>() / 4; ++k)
+		reinterpret_cast<float4 *>(dst)[k] = make_float4(src[4*k], src[4*k+1], src[4*k+2], src[4*k+3]);
+}
+
+// vector reduction into a node tuple (red.global.add.v4.f32, sm_90+)
+template <int N>
+__device__ __forceinline__ void atomic_add_tuple(float *__restrict__ dst, const float *src /* pad4<N>() */)
+{
+#pragma unroll
+	for (int k = 0; k < pad4<N>() / 4; ++k)
+		atomicAdd(reinterpret_cast<float4 *>(dst) + k, make_float4(src[4*k], src[4*k+1], src[4*k+2], src[4*k+3]));
+}
+
 // =====================================================================================
 //  upward pass
 // =====================================================================================
@@ -28,16 +59,14 @@ leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L)
 		for (int j = 0; j < cnt; ++j) { cx += p[3*j]; cy += p[3*j+1]; cz += p[3*j+2]; }
 		if (cnt > 0) { float f = (float)cnt; cx = __fdiv_rn(cx, f); cy = __fdiv_rn(cy, f); cz = __fdiv_rn(cz, f); }
 		t.center[beg + i] = make_float4(cx, cy, cz, 0.f);
-		float M[sym_off(P) > 0 ? sym_off(P) : 1];
+		float M[pad4<sym_off(P)>()];
 #pragma unroll
-		for (int k = 0; k < sym_off(P); ++k) M[k] = 0.f;
+		for (int k = 0; k < pad4<sym_off(P)>(); ++k) M[k] = 0.f;
 		if constexpr (P >= 3)
 			for (int j = 0; j < cnt; ++j)
 				p2m_acc<P>(M, p[3*j] - cx, p[3*j+1] - cy, p[3*j+2] - cz);
 		M[0] = (float)cnt;
-		float *out = t.mpole + (int64_t)(beg + i) * t.sM;
-#pragma unroll
-		for (int k = 0; k < sym_off(P); ++k) out[k] = M[k];
+		store_tuple<sym_off(P)>(t.mpole + (int64_t)(beg + i) * t.sM, M);
 	}
 }
 
@@ -54,24 +83,19 @@ __device__ __forceinline__ void m2m_node(const TreeData &t, int node, int64_t n,
 	float cx = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.x), __fmul_rn(m1, b.x)), mt);
 	float cy = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.y), __fmul_rn(m1, b.y)), mt);
 	float cz = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.z), __fmul_rn(m1, b.z)), mt);
-	float M[sym_off(P) > 0 ? sym_off(P) : 1];
+	float M[pad4<sym_off(P)>()];
 #pragma unroll
-	for (int k = 0; k < sym_off(P); ++k) M[k] = 0.f;
+	for (int k = 0; k < pad4<sym_off(P)>(); ++k) M[k] = 0.f;
 	if constexpr (P >= 3)
 	{
-		float Mi[sym_off(P)];
-		const float *s0 = t.mpole + (int64_t)c0 * t.sM, *s1 = t.mpole + (int64_t)c1 * t.sM;
-#pragma unroll
-		for (int k = 0; k < sym_off(P); ++k) Mi[k] = s0[k];
+		float Mi[pad4<sym_off(P)>()];
+		load_tuple<sym_off(P)>(Mi, t.mpole + (int64_t)c0 * t.sM);
 		m2m_acc<P>(M, Mi, cx - a.x, cy - a.y, cz - a.z);
-#pragma unroll
-		for (int k = 0; k < sym_off(P); ++k) Mi[k] = s1[k];
+		load_tuple<sym_off(P)>(Mi, t.mpole + (int64_t)c1 * t.sM);
 		m2m_acc<P>(M, Mi, cx - b.x, cy - b.y, cz - b.z);
 	}
 	M[0] = mt;
-	float *out = t.mpole + (int64_t)node * t.sM;
-#pragma unroll
-	for (int k = 0; k < sym_off(P); ++k) out[k] = M[k];
+	store_tuple<sym_off(P)>(t.mpole + (int64_t)node * t.sM, M);
 	t.center[node] = make_float4(cx, cy, cz, 0.f);
 }
 
@@ -104,36 +128,32 @@ m2l_kernel(TreeData t, const int2 *__restrict__ list, const u32 *__restrict__ co
 	const u32 npairs = min(*count, cap);
 	for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < npairs; w += gridDim.x * blockDim.x)
 	{
-		const int2 np = list[w];
+		int2 np = list[w];
+		const int flags = (np.x >> kFlagShift) & 3; // bit 0: np.x is a target of this rank, bit 1: np.y
+		np.x &= kNodeMask;
 		const float4 c1 = t.center[np.x], c2 = t.center[np.y];
 		float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z;
 		const float r2 = dx*dx + dy*dy + dz*dz + eps2;
-		const float rinv = rsqrtf(r2);
+		const float rinv = 1.f / sqrtf(r2); // IEEE sqrt and divide like the reference (:636-637); M2L is not flop-bound
 		dx *= rinv; dy *= rinv; dz *= rinv;
-		float M[sym_off(P)], Lq[trl_off(P + 1)];
+		float M[pad4<sym_off(P)>()], Lq[pad4<trl_off(P + 1)>()];
 		// target np.x, source np.y
+		if (flags & 1)
 		{
-			const float *src = t.mpole + (int64_t)np.y * t.sM;
+			load_tuple<sym_off(P)>(M, t.mpole + (int64_t)np.y * t.sM);
 #pragma unroll
-			for (int k = 0; k < sym_off(P); ++k) M[k] = src[k];
-#pragma unroll
-			for (int k = 0; k < trl_off(P + 1); ++k) Lq[k] = 0.f;
+			for (int k = 0; k < pad4<trl_off(P + 1)>(); ++k) Lq[k] = 0.f;
 			m2l_acc<P>(Lq, M, dx, dy, dz, rinv);
-			float *dst = t.local + (int64_t)np.x * t.sL;
-#pragma unroll
-			for (int k = 1; k < trl_off(P + 1); ++k) atomicAdd(dst + k, Lq[k]);
+			atomic_add_tuple<trl_off(P + 1)>(t.local + (int64_t)np.x * t.sL, Lq); // slot 0 receives +0
 		}
 		// target np.y, source np.x
+		if (flags & 2)
 		{
-			const float *src = t.mpole + (int64_t)np.x * t.sM;
+			load_tuple<sym_off(P)>(M, t.mpole + (int64_t)np.x * t.sM);
 #pragma unroll
-			for (int k = 0; k < sym_off(P); ++k) M[k] = src[k];
-#pragma unroll
-			for (int k = 0; k < trl_off(P + 1); ++k) Lq[k] = 0.f;
+			for (int k = 0; k < pad4<trl_off(P + 1)>(); ++k) Lq[k] = 0.f;
 			m2l_acc<P>(Lq, M, -dx, -dy, -dz, rinv);
-			float *dst = t.local + (int64_t)np.y * t.sL;
-#pragma unroll
-			for (int k = 1; k < trl_off(P + 1); ++k) atomicAdd(dst + k, Lq[k]);
+			atomic_add_tuple<trl_off(P + 1)>(t.local + (int64_t)np.y * t.sL, Lq); // slot 0 receives +0
 		}
 	}
 }
@@ -146,24 +166,22 @@ __device__ __forceinline__ void l2l_node(const TreeData &t, int child)
 {
 	const int parent = (child - 1) >> 1;
 	const float4 cp = t.center[parent], cc = t.center[child];
-	float Lp[trl_off(P + 1)], S[sym_off(P + 1)], Lc[trl_off(P + 1)];
-	const float *src = t.local + (int64_t)parent * t.sL;
+	float Lp[pad4<trl_off(P + 1)>()], S[sym_off(P + 1)], Lc[pad4<trl_off(P + 1)>()];
 	float *dst = t.local + (int64_t)child * t.sL;
-#pragma unroll
-	for (int k = 0; k < trl_off(P + 1); ++k) { Lp[k] = src[k]; Lc[k] = dst[k]; }
+	load_tuple<trl_off(P + 1)>(Lp, t.local + (int64_t)parent * t.sL);
+	load_tuple<trl_off(P + 1)>(Lc, dst);
 	S[0] = 0.f;
 	local_expand<P>(S, Lp);
 	l2l_acc<P>(Lc, S, cc.x - cp.x, cc.y - cp.y, cc.z - cp.z);
-#pragma unroll
-	for (int k = 1; k < trl_off(P + 1); ++k) dst[k] = Lc[k];
+	store_tuple<trl_off(P + 1)>(dst, Lc);
 }
 
 // children of level l (i.e. nodes of level l+1) pull from their parents
 template <int P>
-__global__ void __launch_bounds__(128) l2l_level_kernel(TreeData t, int lchild)
+__global__ void __launch_bounds__(128) l2l_level_kernel(TreeData t, int lchild, int first, int count)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < (1 << lchild)) l2l_node<P>(t, kd_beg(lchild) + i);
+	if (i < count) l2l_node<P>(t, kd_beg(lchild) + first + i);
 }
 
 template <int P>
@@ -181,22 +199,20 @@ __global__ void __launch_bounds__(256) l2l_top_kernel(TreeData t, int lfirst, in
 template <int P>
 __global__ void __launch_bounds__(128)
 l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__ acc_near, float *__restrict__ acc_out,
-           const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L)
+           const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L, int64_t j_lo, int64_t j_hi)
 {
 	const float scale = param ? param[0] : 1.f;
 	float k3[3] = {1.f, 1.f, 1.f};
 	if (fuse_elastic && param) { k3[0] = param[3]; k3[1] = param[4]; k3[2] = param[5]; }
 	const int beg = kd_beg(L);
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+	for (int64_t j = j_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < j_hi; j += stride)
 	{
 		// leaf of sorted position j: floor(2^L j / n) (:162-164)
 		const int leaf = (int)((((unsigned long long)j) << L) / (unsigned long long)n);
 		const float4 c = t.center[beg + leaf];
-		float Lq[trl_off(P + 1)], S[sym_off(P + 1)];
-		const float *src = t.local + (int64_t)(beg + leaf) * t.sL;
-#pragma unroll
-		for (int k = 0; k < trl_off(P + 1); ++k) Lq[k] = src[k];
+		float Lq[pad4<trl_off(P + 1)>()], S[sym_off(P + 1)];
+		load_tuple<trl_off(P + 1)>(Lq, t.local + (int64_t)(beg + leaf) * t.sL);
 		S[0] = 0.f;
 		local_expand<P>(S, Lq);
 		const float x = spos[3*j], y = spos[3*j+1], z = spos[3*j+2];
@@ -230,7 +246,7 @@ struct OrderImpl
 		m2l_kernel<P><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2); ++ctx->launches;
 	}
 	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L)
+	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g)
 	{
 		cudaStream_t st = ctx->stream;
 		// locals of levels 0 and 1 stay zero (nothing is ever admissible there); level l+1 pulls from level l >= 1
@@ -239,11 +255,13 @@ struct OrderImpl
 			l2l_top_kernel<P><<<1, 256, 0, st>>>(t, 2, std::min(L, kTopLevels + 1)); ++ctx->launches;
 			for (int l = kTopLevels + 2; l <= L; ++l)
 			{
-				l2l_level_kernel<P><<<((1 << l) + 127) / 128, 128, 0, st>>>(t, l); ++ctx->launches;
+				const int first = l >= g ? r << (l - g) : r >> (g - l), count = l >= g ? 1 << (l - g) : 1;
+				l2l_level_kernel<P><<<(count + 127) / 128, 128, 0, st>>>(t, l, first, count); ++ctx->launches;
 			}
 		}
-		l2p_kernel<P><<<grid_for(n, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
-		                                                                    param, fuse_elastic, n, L);
+		const int64_t j_lo = seg_start(n, r, g), j_hi = seg_start(n, r + 1, g);
+		l2p_kernel<P><<<grid_for(j_hi - j_lo, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
+		                                                                              param, fuse_elastic, n, L, j_lo, j_hi);
 		++ctx->launches;
 	}
 };

@@ -249,14 +249,17 @@ g_m2l_kernel(TreeData t, const int2 *__restrict__ list, const unsigned *__restri
 	const int offL = g_trl_off(P + 1);
 	for (unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < npairs; w += gridDim.x * blockDim.x)
 	{
-		const int2 np = list[w];
+		int2 np = list[w];
+		const int flags = (np.x >> kFlagShift) & 3;
+		np.x &= kNodeMask;
 		const float4 c1 = t.center[np.x], c2 = t.center[np.y];
 		float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z;
-		const float rinv = rsqrtf(dx*dx + dy*dy + dz*dz + eps2);
+		const float rinv = 1.f / sqrtf(dx*dx + dy*dy + dz*dz + eps2);
 		dx *= rinv; dy *= rinv; dz *= rinv;
 		float Lq[kMaxTrl];
 		for (int dir = 0; dir < 2; ++dir)
 		{
+			if (!((flags >> dir) & 1)) continue;
 			const int tgt = dir ? np.y : np.x, src = dir ? np.x : np.y;
 			const float s = dir ? -1.f : 1.f;
 			for (int k = 0; k < offL; ++k) Lq[k] = 0.f;
@@ -279,10 +282,10 @@ __device__ void g_l2l_node(const TreeData &t, int child, int P)
 	for (int k = 1; k < offL; ++k) dst[k] = Lc[k];
 }
 
-__global__ void __launch_bounds__(128) g_l2l_level_kernel(TreeData t, int lchild, int P)
+__global__ void __launch_bounds__(128) g_l2l_level_kernel(TreeData t, int lchild, int first, int count, int P)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < (1 << lchild)) g_l2l_node(t, kd_beg(lchild) + i, P);
+	if (i < count) g_l2l_node(t, kd_beg(lchild) + first + i, P);
 }
 
 __global__ void __launch_bounds__(256) g_l2l_top_kernel(TreeData t, int lfirst, int llast, int P)
@@ -297,14 +300,14 @@ __global__ void __launch_bounds__(256) g_l2l_top_kernel(TreeData t, int lfirst, 
 
 __global__ void __launch_bounds__(128)
 g_l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__ acc_near, float *__restrict__ acc_out,
-             const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L, int P)
+             const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L, int P, int64_t j_lo, int64_t j_hi)
 {
 	const float scale = param ? param[0] : 1.f;
 	float k3[3] = {1.f, 1.f, 1.f};
 	if (fuse_elastic && param) { k3[0] = param[3]; k3[1] = param[4]; k3[2] = param[5]; }
 	const int beg = kd_beg(L);
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-	for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+	for (int64_t j = j_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < j_hi; j += stride)
 	{
 		const int leaf = (int)((((unsigned long long)j) << L) / (unsigned long long)n);
 		const float4 c = t.center[beg + leaf];
@@ -340,7 +343,7 @@ struct GenImpl
 		g_m2l_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2, P); ++ctx->launches;
 	}
 	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L)
+	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g)
 	{
 		cudaStream_t st = ctx->stream;
 		if (L >= 2)
@@ -348,11 +351,13 @@ struct GenImpl
 			g_l2l_top_kernel<<<1, 256, 0, st>>>(t, 2, std::min(L, kTopLevels + 1), P); ++ctx->launches;
 			for (int l = kTopLevels + 2; l <= L; ++l)
 			{
-				g_l2l_level_kernel<<<((1 << l) + 127) / 128, 128, 0, st>>>(t, l, P); ++ctx->launches;
+				const int first = l >= g ? r << (l - g) : r >> (g - l), count = l >= g ? 1 << (l - g) : 1;
+				g_l2l_level_kernel<<<(count + 127) / 128, 128, 0, st>>>(t, l, first, count, P); ++ctx->launches;
 			}
 		}
-		g_l2p_kernel<<<grid_for(n, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
-		                                                                  param, fuse_elastic, n, L, P);
+		const int64_t j_lo = seg_start(n, r, g), j_hi = seg_start(n, r + 1, g);
+		g_l2p_kernel<<<grid_for(j_hi - j_lo, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
+		                                                                            param, fuse_elastic, n, L, P, j_lo, j_hi);
 		++ctx->launches;
 	}
 };

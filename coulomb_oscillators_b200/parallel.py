@@ -36,3 +36,57 @@ def sharded_direct3(compute_shard, pos, n, group=None):
     b, e = shard_range(n, rank, world)
     acc = compute_shard(rank, world)
     return all_gather_shards(acc[b:e].contiguous(), n, group)
+
+
+def fmm_leapfrog_sharded(ctx, buf, n, d_param, dt, nsteps, group=None):
+    """Leapfrog steps of coulombOscillatorFMMKD3 over `world` GPUs (one process per GPU).
+
+    Partition: rank r of 2^g owns the subtree of kd node (g, r), i.e. the
+    contiguous tree-order range [ceil(n r/w), ceil(n (r+1)/w)) of particles.  Every rank keeps the
+    full position array: the tree (build, P2M/M2M, traversal) is replicated, while P2P, M2L,
+    L2L/L2P and the kick/drift run on the rank's own range only (ctx.cfg.rank/world).  Exchange per
+    step: one all-gather of the drifted positions; on tree-rebuild steps also of the velocities,
+    because the rebuild permutes the whole state.
+
+    buf: torch float32 tensor [pos | vel | acc] (9n) on this rank's GPU, identical on all ranks at
+    entry and with acc already computed (main3.cu:835-839); ctx: Context(rank=r, world=w, unsort=0)."""
+    import torch
+    import torch.distributed as dist
+    from ._lib import LEAPFROG, EVAL_COULOMB_FMM3_KD  # noqa: F401
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    assert ctx.cfg.rank == rank and ctx.cfg.world == world and ctx.cfg.unsort == 0
+    b, e = shard_range(n, rank, world)
+    cnt = e - b
+    pos, vel, acc = buf[:3 * n], buf[3 * n:6 * n], buf[6 * n:]
+    sizes = shard_sizes(n, world)
+    equal = len(set(sizes)) == 1
+    dtf = float(np.float32(dt))
+    half = float(np.float32(np.longdouble(dtf) * np.longdouble(0.5)))
+
+    def gather(full, lo, hi):
+        if world == 1:
+            return
+        local = full[3 * lo:3 * hi].clone()
+        if equal:
+            dist.all_gather_into_tensor(full, local, group=group)
+        else:
+            pad = 3 * max(sizes)
+            tmp = torch.zeros(pad, dtype=full.dtype, device=full.device)
+            tmp[:local.numel()] = local
+            out = [torch.empty_like(tmp) for _ in range(world)]
+            dist.all_gather(out, tmp, group=group)
+            full.copy_(torch.cat([o[:3 * s] for o, s in zip(out, sizes)]))
+        torch.cuda.current_stream().synchronize()
+
+    p0 = buf.data_ptr()
+    for _ in range(nsteps):
+        ctx.step(p0 + 4 * (3 * n + 3 * b), p0 + 4 * (6 * n + 3 * b), half, cnt)   # v += a dt/2   (own range)
+        ctx.step(p0 + 4 * (3 * b), p0 + 4 * (3 * n + 3 * b), dtf, cnt)            # x += v dt
+        gather(pos, b, e)
+        if ctx.fmm_info().counter % ctx.cfg.tree_steps == 0:
+            gather(vel, b, e)                                                     # the rebuild permutes everything
+        ctx.coulomb_fmm3_kd(p0, p0 + 4 * 6 * n, n, d_param)                       # a = f(x)     (own range written)
+        ctx.step(p0 + 4 * (3 * n + 3 * b), p0 + 4 * (6 * n + 3 * b), half, cnt)   # v += a dt/2
+    gather(vel, b, e)
+    gather(acc, b, e)

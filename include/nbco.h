@@ -147,6 +147,8 @@ typedef struct nbco_fmm_info
 	int32_t rebuilt;       /* 1 if the last evaluation rebuilt the tree */
 	int32_t mlt_max;
 	int64_t kernel_launches; /* kernels launched by this context so far */
+	int32_t counter;       /* FMM evaluations since the last re-plan; the next one rebuilds iff counter % tree_steps == 0 */
+	int32_t reserved;
 } nbco_fmm_info;
 
 int nbco_fmm_get_info(nbco_ctx *ctx, nbco_fmm_info *info);
