@@ -49,7 +49,6 @@ __global__ void __launch_bounds__(256) gather3_kernel(const float *__restrict__ 
 struct TravArgs
 {
 	const float4 *center;
-	const float *size2;
 	const float *mfac;    // [level][2]: MAC factor M for the low / high multiplicity of the level
 	int2 *p2p, *m2l, *front_in, *front_out;
 	u32 *cnt;             // [0] p2p, [1] m2l, [2..4] frontier sizes (rotating)
@@ -81,7 +80,7 @@ __device__ __forceinline__ bool mac_ok(const TravArgs &a, int n1, int n2)
 	float4 c1 = a.center[n1], c2 = a.center[n2];
 	float dx = __fsub_rn(c2.x, c1.x), dy = __fsub_rn(c2.y, c1.y), dz = __fsub_rn(c2.z, c1.z);
 	float dist2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-	float sz = fmaxf(a.size2[n1], a.size2[n2]);
+	float sz = fmaxf(c1.w, c2.w);
 	int l1, l2;
 	int m1 = node_mult(a.n, n1, l1), m2 = node_mult(a.n, n2, l2);
 	int lv = m1 >= m2 ? l1 : l2, mm = m1 >= m2 ? m1 : m2;
@@ -108,58 +107,128 @@ __device__ __forceinline__ u32 warp_append(u32 *counter, int count)
 	return base + (u32)(incl - count);
 }
 
+// one pair of the dual traversal (fmm_dualTraversal_cpu, :581-610; m2l_first as in the GPU kernel :504-542)
+// returns 0 nothing, 1 p2p, 2 m2l, 3 self split, 4 split y, 5 split x; flags = which side is a target here
+__device__ __forceinline__ int classify_pair(const TravArgs &a, int2 np, int &flags)
+{
+	int kind;
+	const bool xl = 2*np.x + 1 >= a.ntot, yl = 2*np.y + 1 >= a.ntot;
+	if (!a.m2l_first && xl && yl) kind = (np.x != np.y) ? 1 : 0;
+	else if (np.x == np.y && !xl) kind = 3;
+	else if (np.x != np.y && mac_ok(a, np.x, np.y)) kind = 2;
+	else if (xl && yl) kind = (np.x != np.y) ? 1 : 0;
+	else if (xl || (!yl && a.center[np.x].w <= a.center[np.y].w)) kind = 4;
+	else kind = 5;
+	// bit 0: np.x is a target of this rank, bit 1: np.y is; untouched pairs (and their
+	// descendants) are dropped.  With one rank every node is a target (flags = 3).
+	flags = 0;
+	if (kind) flags = (node_mine(a, np.x) ? 1 : 0) | (node_mine(a, np.y) ? 2 : 0);
+	return flags ? kind : 0;
+}
+
+__device__ __forceinline__ int expand_pair(int kind, int2 np, int2 *out)
+{
+	if (kind == 3)
+	{
+		out[0] = make_int2(2*np.x + 1, 2*np.x + 1);
+		out[1] = make_int2(2*np.x + 1, 2*np.x + 2);
+		out[2] = make_int2(2*np.x + 2, 2*np.x + 2);
+		return 3;
+	}
+	if (kind == 4) { out[0] = make_int2(np.x, 2*np.y + 1); out[1] = make_int2(np.x, 2*np.y + 2); return 2; }
+	if (kind == 5) { out[0] = make_int2(2*np.x + 1, np.y); out[1] = make_int2(2*np.x + 2, np.y); return 2; }
+	return 0;
+}
+
+// level-synchronous round.  Appends are aggregated per CTA: the three output counters (p2p list, m2l
+// list, next frontier) receive ONE atomic each per 256 classified pairs -- per-warp atomics on the same
+// three addresses serialise in L2 and dominated the big rounds (profiles/r01_notes.md).
 __global__ void __launch_bounds__(256) traverse_round_kernel(TravArgs a, int round)
 {
+	__shared__ u32 wtot[8][3];
+	__shared__ u32 base[3];
 	u32 *cin = a.cnt + 2 + round % 3, *cout = a.cnt + 2 + (round + 1) % 3, *cnext = a.cnt + 2 + (round + 2) % 3;
 	if (blockIdx.x == 0 && threadIdx.x == 0) *cnext = 0; // nobody touches it during this round
 	const u32 nin = min(*cin, a.cap_front);
-	const u32 nwork = (nin + 31u) & ~31u; // whole warps stay converged for the shuffles
-	for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += gridDim.x * blockDim.x)
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (u32 w0 = blockIdx.x * blockDim.x; w0 < nin; w0 += gridDim.x * blockDim.x)
 	{
-		int kind = 0; // 0 nothing, 1 p2p, 2 m2l, 3 self split, 4 split y, 5 split x
+		const u32 w = w0 + threadIdx.x;
+		int kind = 0, flags = 0;
 		int2 np = make_int2(0, 0);
-		if (w < nin)
+		if (w < nin) { np = a.front_in[w]; kind = classify_pair(a, np, flags); }
+		int2 kids[3];
+		const int nf = expand_pair(kind, np, kids);
+		// packed per-lane counts: bits 0..9 p2p, 10..19 m2l, 20..31 frontier entries
+		const u32 mine = (kind == 1 ? 1u : 0u) | (kind == 2 ? 1u << 10 : 0u) | ((u32)nf << 20);
+		u32 incl = mine;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
 		{
-			np = a.front_in[w];
-			const bool xl = 2*np.x + 1 >= a.ntot, yl = 2*np.y + 1 >= a.ntot;
-			if (!a.m2l_first && xl && yl) kind = (np.x != np.y) ? 1 : 0;
-			else if (np.x == np.y && !xl) kind = 3;
-			else if (np.x != np.y && mac_ok(a, np.x, np.y)) kind = 2;
-			else if (xl && yl) kind = (np.x != np.y) ? 1 : 0;
-			else if (xl || (!yl && a.size2[np.x] <= a.size2[np.y])) kind = 4;
-			else kind = 5;
+			u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += v;
 		}
-		// bit 0: np.x is a target of this rank, bit 1: np.y is; untouched pairs (and their
-		// descendants) are dropped.  With one rank every node is a target (flags = 3).
-		int flags = 0;
-		if (kind) flags = (node_mine(a, np.x) ? 1 : 0) | (node_mine(a, np.y) ? 2 : 0);
-		if (!flags) kind = 0;
+		if (lane == 31) { wtot[warp][0] = incl & 1023u; wtot[warp][1] = (incl >> 10) & 1023u; wtot[warp][2] = incl >> 20; }
+		__syncthreads();
+		if (threadIdx.x < 3)
+		{
+			u32 tot = 0;
+			for (int i = 0; i < 8; ++i) tot += wtot[i][threadIdx.x];
+			u32 *c = threadIdx.x == 0 ? a.cnt + 0 : (threadIdx.x == 1 ? a.cnt + 1 : cout);
+			base[threadIdx.x] = tot ? atomicAdd(c, tot) : 0u;
+		}
+		__syncthreads();
+		const u32 excl = incl - mine;
+		u32 s1 = base[0] + (excl & 1023u), s2 = base[1] + ((excl >> 10) & 1023u), s3 = base[2] + (excl >> 20);
+		for (int i = 0; i < warp; ++i) { s1 += wtot[i][0]; s2 += wtot[i][1]; s3 += wtot[i][2]; }
+		const int2 tagged = make_int2(np.x | (flags << kFlagShift), np.y);
+		if (kind == 1 && s1 < a.cap_p2p) a.p2p[s1] = tagged;
+		if (kind == 2 && s2 < a.cap_m2l) a.m2l[s2] = tagged;
+		if (nf && s3 + nf > a.cap_front) a.cnt[5] = 1u; // sticky: a frontier did not fit
+		if (nf && s3 + nf <= a.cap_front)
+			for (int k = 0; k < nf; ++k) a.front_out[s3 + k] = kids[k];
+		__syncthreads(); // wtot / base are reused by the next chunk
+	}
+}
+
+// depth-first completion: every lane takes pairs of the last frontier from a global counter and
+// walks their subtrees with a private stack (<= 4L+3 entries); no more launches, no frontier traffic
+constexpr int kDfsStack = 112;
+
+__global__ void __launch_bounds__(128) traverse_dfs_kernel(TravArgs a, int round)
+{
+	const u32 nin = min(a.cnt[2 + round % 3], a.cap_front);
+	const int lane = threadIdx.x & 31;
+	const u32 lt_mask = (1u << lane) - 1u;
+	int2 stack[kDfsStack];
+	int top = 0;
+	while (true)
+	{
+		const bool want = top == 0;
+		const u32 wmask = __ballot_sync(0xffffffffu, want);
+		if (wmask)
+		{
+			u32 base = 0;
+			const int leader = __ffs(wmask) - 1;
+			if (lane == leader) base = atomicAdd(a.cnt + 6, (u32)__popc(wmask));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			const u32 idx = base + __popc(wmask & lt_mask);
+			if (want && idx < nin) stack[top++] = a.front_in[idx];
+		}
+		const bool has = top > 0;
+		if (!__any_sync(0xffffffffu, has)) break;
+		int kind = 0, flags = 0;
+		int2 np = make_int2(0, 0);
+		if (has) { np = stack[--top]; kind = classify_pair(a, np, flags); }
 		const int2 tagged = make_int2(np.x | (flags << kFlagShift), np.y);
 		u32 s1 = warp_append(a.cnt + 0, kind == 1);
 		if (kind == 1 && s1 < a.cap_p2p) a.p2p[s1] = tagged;
 		u32 s2 = warp_append(a.cnt + 1, kind == 2);
 		if (kind == 2 && s2 < a.cap_m2l) a.m2l[s2] = tagged;
-		int nf = kind == 3 ? 3 : (kind >= 4 ? 2 : 0);
-		u32 s3 = warp_append(cout, nf);
-		if (nf && s3 + nf > a.cap_front) a.cnt[5] = 1u; // sticky: a frontier did not fit
-		if (nf && s3 + nf <= a.cap_front)
+		if (kind >= 3)
 		{
-			if (kind == 3)
-			{
-				a.front_out[s3]     = make_int2(2*np.x + 1, 2*np.x + 1);
-				a.front_out[s3 + 1] = make_int2(2*np.x + 1, 2*np.x + 2);
-				a.front_out[s3 + 2] = make_int2(2*np.x + 2, 2*np.x + 2);
-			}
-			else if (kind == 4)
-			{
-				a.front_out[s3]     = make_int2(np.x, 2*np.y + 1);
-				a.front_out[s3 + 1] = make_int2(np.x, 2*np.y + 2);
-			}
-			else
-			{
-				a.front_out[s3]     = make_int2(2*np.x + 1, np.y);
-				a.front_out[s3 + 1] = make_int2(2*np.x + 2, np.y);
-			}
+			if (top + 3 <= kDfsStack) top += expand_pair(kind, np, stack + top);
+			else a.cnt[5] = 1u;
 		}
 	}
 }
@@ -169,7 +238,7 @@ __global__ void traverse_init_kernel(int2 *front, u32 *cnt)
 	if (threadIdx.x == 0 && blockIdx.x == 0)
 	{
 		front[0] = make_int2(0, 0);
-		cnt[0] = 0; cnt[1] = 0; cnt[2] = 1; cnt[3] = 0; cnt[4] = 0; cnt[5] = 0;
+		cnt[0] = 0; cnt[1] = 0; cnt[2] = 1; cnt[3] = 0; cnt[4] = 0; cnt[5] = 0; cnt[6] = 0;
 	}
 }
 
@@ -337,7 +406,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	const int64_t n = p.n;
 	const int L = p.L;
 	const nbco_config &c = ctx->cfg;
-	TreeData t{p.center.as<float4>(), p.mpole.as<float>(), p.local.as<float>(), p.sM, p.sL};
+	TreeData t{p.center.as<float4>(), p.kd.size2.as<float>(), p.mpole.as<float>(), p.local.as<float>(), p.sM, p.sL};
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_BUILD], st));
 	const float *spos = d_pos; // tree-ordered positions the passes read
@@ -360,7 +429,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_TRAVERSE], st));
 	TravArgs a;
-	a.center = t.center; a.size2 = p.kd.size2.as<float>(); a.mfac = p.mfac.as<float>();
+	a.center = t.center; a.mfac = p.mfac.as<float>();
 	a.p2p = p.p2p.as<int2>(); a.m2l = p.m2l.as<int2>();
 	a.cnt = p.cnt.as<u32>();
 	a.cap_p2p = a.cap_m2l = p.cap_list; a.cap_front = p.cap_front;
@@ -371,12 +440,19 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	const int leaf_lo = c.rank << (L - g), leaf_hi = (c.rank + 1) << (L - g);
 	a.sh_lo = seg_start(n, c.rank, g); a.sh_hi = seg_start(n, c.rank + 1, g);
 	traverse_init_kernel<<<1, 32, 0, st>>>(p.frontA.as<int2>(), a.cnt); LAUNCHED(ctx);
-	const int rounds = 2 * L + 2;
-	for (int r = 0; r < rounds; ++r)
+	// breadth first while the frontier is small, then one depth-first kernel finishes every subtree
+	static int env_rounds = -2;
+	if (env_rounds == -2) { const char *e = getenv("NBCO_TRAV_ROUNDS"); env_rounds = e ? atoi(e) : -1; }
+	// measured on B200 (profiles/r01_notes.md): the depth-first tail is 2-25x slower than breadth-first rounds
+	// (private stacks in local memory, divergent subtrees), so by default every round is breadth first
+	const int rounds = env_rounds >= 0 ? std::min(env_rounds, 2 * L + 2) : 2 * L + 2;
+	for (int r = 0; r <= rounds; ++r)
 	{
 		a.front_in = (r & 1) ? p.frontB.as<int2>() : p.frontA.as<int2>();
 		a.front_out = (r & 1) ? p.frontA.as<int2>() : p.frontB.as<int2>();
-		traverse_round_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, r); LAUNCHED(ctx);
+		if (r < rounds) traverse_round_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, r);
+		else traverse_dfs_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(a, r);
+		LAUNCHED(ctx);
 	}
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_P2P], st));
@@ -388,21 +464,20 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 #define P2P_LAUNCH(G)                                                                                              \
 		do {                                                                                                       \
 			p2p_kernel<G, false><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2, leaf_lo, leaf_hi); \
-			p2p_kernel<G, true><<<blocks, 256, 0, st>>>(nullptr, nullptr, 0, spos, accn, n, L, c.eps2, leaf_lo, leaf_hi);        \
 		} while (0)
 		if (p.mlt_max <= 4) P2P_LAUNCH(4);
 		else if (p.mlt_max <= 8) P2P_LAUNCH(8);
 		else if (p.mlt_max <= 16) P2P_LAUNCH(16);
 		else P2P_LAUNCH(32);
 #undef P2P_LAUNCH
-		ctx->launches += 2;
+		ctx->launches += 1;
 	}
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_M2L], st));
 	ops.m2l(ctx, t, a.m2l, a.cnt + 1, a.cap_m2l, c.eps2);
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_DOWNWARD], st));
-	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g);
+	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll);
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_COUNT], st));
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;

@@ -87,7 +87,8 @@ __device__ __forceinline__ void write_box(const TreeGeom &g, int node, const flo
 
 struct TreeData
 {
-	float4 *center;   // xyz, w unused
+	float4 *center;   // xyz = centre of charge, w = kd_size of the node's box (read by the MAC)
+	const float *size2;
 	float *mpole;     // sM floats per node, symmetric tuple orders 0..P-1
 	float *local;     // sL floats per node, traceless tuple orders 0..P
 	int sM, sL;
@@ -99,12 +100,35 @@ struct KdTree
 	int64_t n = 0;
 	int L = 0, lt = 0;
 	DevBuf lbound, rbound, size2, splitdim, chain;   // per node
-	DevBuf keys, idxA, idxB, tie, hist, sel, cur, spos, perm, bbox;
+	DevBuf keys, idxA, idxB, tie, hist, sel, cur, spos, perm, bbox, soa;
 	bool bottom_attr = false;
 };
 int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L);
 int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos);
 void kd_release(KdTree &t);
+
+// intra-leaf near field of one particle (fmm_p2p3_self_kdtree, :1048-1120): the other particles of its
+// leaf, read through L1 (a leaf is 1-2 cache lines); i = j contributes exactly 0
+__device__ __forceinline__ void self_p2p(float *f, const float *__restrict__ spos, int64_t j, int leaf,
+                                         float x, float y, float z, int64_t n, int L, float eps2)
+{
+	const int64_t s0 = seg_start(n, leaf, L), s1 = seg_start(n, leaf + 1, L);
+	float ax = 0.f, ay = 0.f, az = 0.f;
+	for (int64_t k = s0; k < s1; ++k)
+	{
+		const float dx = x - spos[3*k], dy = y - spos[3*k+1], dz = z - spos[3*k+2];
+		float r2 = fmaf(dx, dx, eps2);
+		r2 = fmaf(dy, dy, r2);
+		r2 = fmaf(dz, dz, r2);
+		float w;
+		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(r2));
+		w = w * fmaf(-0.5f * r2 * w, w, 1.5f);
+		const float w3 = (w * w) * w;
+		ax = fmaf(dx, w3, ax); ay = fmaf(dy, w3, ay); az = fmaf(dz, w3, az);
+	}
+	(void)j;
+	f[0] += ax; f[1] += ay; f[2] += az;
+}
 
 // Order-specific passes (one translation unit per order: the unrolled templates are expensive
 // to compile, the reference's single TU takes > 4 min).
@@ -114,7 +138,8 @@ struct OrderOps
 	void (*m2l)(nbco_ctx *ctx, TreeData t, const int2 *list, const unsigned *count, unsigned cap, float eps2);
 	// rank r of 2^g ranks pushes locals down its own subtree (plus the ancestors of its root) only
 	void (*downward)(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                 const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g);
+	                 const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g,
+	                 float eps2, int coll);
 };
 const OrderOps *order_ops(int order);
 

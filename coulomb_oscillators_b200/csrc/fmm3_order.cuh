@@ -58,7 +58,7 @@ leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L)
 		float cx = 0.f, cy = 0.f, cz = 0.f;
 		for (int j = 0; j < cnt; ++j) { cx += p[3*j]; cy += p[3*j+1]; cz += p[3*j+2]; }
 		if (cnt > 0) { float f = (float)cnt; cx = __fdiv_rn(cx, f); cy = __fdiv_rn(cy, f); cz = __fdiv_rn(cz, f); }
-		t.center[beg + i] = make_float4(cx, cy, cz, 0.f);
+		t.center[beg + i] = make_float4(cx, cy, cz, t.size2[beg + i]);
 		float M[pad4<sym_off(P)>()];
 #pragma unroll
 		for (int k = 0; k < pad4<sym_off(P)>(); ++k) M[k] = 0.f;
@@ -96,7 +96,7 @@ __device__ __forceinline__ void m2m_node(const TreeData &t, int node, int64_t n,
 	}
 	M[0] = mt;
 	store_tuple<sym_off(P)>(t.mpole + (int64_t)node * t.sM, M);
-	t.center[node] = make_float4(cx, cy, cz, 0.f);
+	t.center[node] = make_float4(cx, cy, cz, t.size2[node]);
 }
 
 template <int P>
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) l2l_top_kernel(TreeData t, int lfirst, in
 template <int P>
 __global__ void __launch_bounds__(128)
 l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__ acc_near, float *__restrict__ acc_out,
-           const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L, int64_t j_lo, int64_t j_hi)
+           const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L, int64_t j_lo, int64_t j_hi, float eps2, int coll)
 {
 	const float scale = param ? param[0] : 1.f;
 	float k3[3] = {1.f, 1.f, 1.f};
@@ -218,6 +218,7 @@ l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__
 		const float x = spos[3*j], y = spos[3*j+1], z = spos[3*j+2];
 		float f[3];
 		l2p_field<P>(f, S, x - c.x, y - c.y, z - c.z);
+		if (coll) self_p2p(f, spos, j, leaf, x, y, z, n, L, eps2);
 		float ax = (acc_near[3*j] + f[0]) * scale, ay = (acc_near[3*j+1] + f[1]) * scale, az = (acc_near[3*j+2] + f[2]) * scale;
 		if (fuse_elastic) { ax = fmaf(-k3[0], x, ax); ay = fmaf(-k3[1], y, ay); az = fmaf(-k3[2], z, az); }
 		const int64_t o = perm_or_null ? (int64_t)perm_or_null[j] : j;
@@ -246,7 +247,7 @@ struct OrderImpl
 		m2l_kernel<P><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2); ++ctx->launches;
 	}
 	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g)
+	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll)
 	{
 		cudaStream_t st = ctx->stream;
 		// locals of levels 0 and 1 stay zero (nothing is ever admissible there); level l+1 pulls from level l >= 1
@@ -261,7 +262,7 @@ struct OrderImpl
 		}
 		const int64_t j_lo = seg_start(n, r, g), j_hi = seg_start(n, r + 1, g);
 		l2p_kernel<P><<<grid_for(j_hi - j_lo, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
-		                                                                              param, fuse_elastic, n, L, j_lo, j_hi);
+		                                                                              param, fuse_elastic, n, L, j_lo, j_hi, eps2, coll);
 		++ctx->launches;
 	}
 };

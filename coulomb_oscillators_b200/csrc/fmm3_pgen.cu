@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) g_leaf_p2m_kernel(TreeData t, const float
 		float cx = 0.f, cy = 0.f, cz = 0.f;
 		for (int j = 0; j < cnt; ++j) { cx += p[3*j]; cy += p[3*j+1]; cz += p[3*j+2]; }
 		if (cnt > 0) { float f = (float)cnt; cx = __fdiv_rn(cx, f); cy = __fdiv_rn(cy, f); cz = __fdiv_rn(cz, f); }
-		t.center[beg + i] = make_float4(cx, cy, cz, 0.f);
+		t.center[beg + i] = make_float4(cx, cy, cz, t.size2[beg + i]);
 		float M[kMaxSym];
 		for (int k = 0; k < offM; ++k) M[k] = 0.f;
 		if (P >= 3)
@@ -223,7 +223,7 @@ __device__ void g_m2m_node(const TreeData &t, int node, int64_t n, int l, int i,
 	M[0] = mt;
 	float *out = t.mpole + (int64_t)node * t.sM;
 	for (int k = 0; k < offM; ++k) out[k] = M[k];
-	t.center[node] = make_float4(cx, cy, cz, 0.f);
+	t.center[node] = make_float4(cx, cy, cz, t.size2[node]);
 }
 
 __global__ void __launch_bounds__(128) g_m2m_level_kernel(TreeData t, int64_t n, int l, int P)
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) g_l2l_top_kernel(TreeData t, int lfirst, 
 
 __global__ void __launch_bounds__(128)
 g_l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__ acc_near, float *__restrict__ acc_out,
-             const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L, int P, int64_t j_lo, int64_t j_hi)
+             const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L, int P, int64_t j_lo, int64_t j_hi, float eps2, int coll)
 {
 	const float scale = param ? param[0] : 1.f;
 	float k3[3] = {1.f, 1.f, 1.f};
@@ -316,6 +316,7 @@ g_l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict
 		const float x = spos[3*j], y = spos[3*j+1], z = spos[3*j+2];
 		float f[3];
 		g_l2p_field(f, S, P, x - c.x, y - c.y, z - c.z);
+		if (coll) self_p2p(f, spos, j, leaf, x, y, z, n, L, eps2);
 		float ax = (acc_near[3*j] + f[0]) * scale, ay = (acc_near[3*j+1] + f[1]) * scale, az = (acc_near[3*j+2] + f[2]) * scale;
 		if (fuse_elastic) { ax = fmaf(-k3[0], x, ax); ay = fmaf(-k3[1], y, ay); az = fmaf(-k3[2], z, az); }
 		const int64_t o = perm_or_null ? (int64_t)perm_or_null[j] : j;
@@ -343,7 +344,7 @@ struct GenImpl
 		g_m2l_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2, P); ++ctx->launches;
 	}
 	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g)
+	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll)
 	{
 		cudaStream_t st = ctx->stream;
 		if (L >= 2)
@@ -357,7 +358,7 @@ struct GenImpl
 		}
 		const int64_t j_lo = seg_start(n, r, g), j_hi = seg_start(n, r + 1, g);
 		g_l2p_kernel<<<grid_for(j_hi - j_lo, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
-		                                                                            param, fuse_elastic, n, L, P, j_lo, j_hi);
+		                                                                            param, fuse_elastic, n, L, P, j_lo, j_hi, eps2, coll);
 		++ctx->launches;
 	}
 };

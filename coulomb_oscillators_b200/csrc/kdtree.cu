@@ -111,9 +111,20 @@ __device__ __forceinline__ void hist_flush(const u32 *sh, u32 *__restrict__ gh, 
 	}
 }
 
+// x[n] | y[n] | z[n]: a level's keys are gathered from ONE coordinate array per segment (n*4 B, L2-sized)
+// instead of 12-byte-strided AoS rows
+__global__ void __launch_bounds__(256) to_soa_kernel(const float *__restrict__ pos, float *__restrict__ soa, int64_t n)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+	{
+		soa[i] = pos[3*i]; soa[n + i] = pos[3*i+1]; soa[2*n + i] = pos[3*i+2];
+	}
+}
+
 // keys of level l (evalKeys_kdtree, :158-192) + histogram of key bits 31..21
 __global__ void __launch_bounds__(kSelThreads)
-keygen_hist_kernel(const float *__restrict__ pos, const int *__restrict__ splitdim, const u32 *__restrict__ idx,
+keygen_hist_kernel(const float *__restrict__ soa, const int *__restrict__ splitdim, const u32 *__restrict__ idx,
                    u32 *__restrict__ keys, u32 *__restrict__ hist, int64_t n, int l, int tps)
 {
 	__shared__ u32 sh[kBins0];
@@ -129,7 +140,7 @@ keygen_hist_kernel(const float *__restrict__ pos, const int *__restrict__ splitd
 		if (valid)
 		{
 			const int64_t id = idx ? (int64_t)idx[j] : j;
-			key = ordered_bits(pos[3 * id + axis]);
+			key = ordered_bits(soa[(int64_t)axis * n + id]);
 			keys[j] = key;
 		}
 		hist_add(sh, key >> 21, valid);
@@ -379,13 +390,21 @@ struct WarpSortCtx
 	const BottomSmem *s; const int *chain_arr; const u32 *idx_in; int64_t s0; int node0; int base; int logB;
 };
 
-__device__ __forceinline__ bool ws_less(u64 a, u64 b, int e, const WarpSortCtx &c)
+// Words of different keys order like plain u64 (the key sits above the slot).  Equal keys with different
+// slots are rare: the slow path (rest of the total order) runs only when some lane of the warp sees one.
+__device__ __forceinline__ bool ws_first_less(u64 a, u64 b, int e, const WarpSortCtx &c)
 {
-	u64 ka = a >> 13, kb = b >> 13;
-	if (ka != kb) return ka < kb;
-	if (a == ~0ull) return false;
-	const int chain = c.chain_arr[c.node0 + ((c.base + e) >> c.logB)];
-	return slot_tie_less(*c.s, (u32)a & kSlotMask, (u32)b & kSlotMask, chain, c.idx_in, c.s0);
+	bool less = a < b;
+	const bool tie = ((a ^ b) >> 13) == 0 && a != b;
+	if (__any_sync(0xffffffffu, tie))
+	{
+		if (tie)
+		{
+			const int chain = c.chain_arr[c.node0 + ((c.base + e) >> c.logB)];
+			less = slot_tie_less(*c.s, (u32)a & kSlotMask, (u32)b & kSlotMask, chain, c.idx_in, c.s0);
+		}
+	}
+	return less;
 }
 
 template <int M>
@@ -397,9 +416,11 @@ __device__ __forceinline__ void ws_reg_stage(u64 (&v)[8], int lane, int k, int B
 		{
 			const int e = i * 32 + lane;
 			const bool asc = (e & k) == 0 || k == B;
-			u64 a = v[i], b = v[i | M];
-			const bool sw = asc ? ws_less(b, a, e, c) : ws_less(a, b, e, c);
-			if (sw) { v[i] = b; v[i | M] = a; }
+			const u64 a = v[i], b = v[i | M];
+			const bool b_first = ws_first_less(b, a, e, c);
+			const bool sw = (asc == b_first) && a != b;
+			v[i] = sw ? b : a;
+			v[i | M] = sw ? a : b;
 		}
 }
 
@@ -416,17 +437,18 @@ __device__ __forceinline__ void warp_sort_blocks(u64 (&v)[8], int lane, int B, c
 			}
 			else
 			{
+				const bool lower = (lane & jj) == 0;
 #pragma unroll
 				for (int i = 0; i < 8; ++i)
 				{
 					const int e = i * 32 + lane;
-					const u64 o = __shfl_xor_sync(0xffffffffu, v[i], jj);
+					const u64 a = v[i];
+					const u64 o = __shfl_xor_sync(0xffffffffu, a, jj);
 					const bool asc = (e & k) == 0 || k == B;
-					const bool lower = (e & jj) == 0;
+					const bool o_first = ws_first_less(o, a, e, c);
 					// the lower index keeps the smaller word when ascending
-					const bool o_less = ws_less(o, v[i], e, c);
-					const bool take = (lower == asc) ? o_less : (!o_less && o != v[i]);
-					if (take) v[i] = o;
+					const bool take = ((lower == asc) == o_first) && o != a;
+					v[i] = take ? o : a;
 				}
 			}
 		}
@@ -561,24 +583,33 @@ kd_bottom_kernel(TreeGeom g, const float *__restrict__ pos, const u32 *__restric
 #pragma unroll
 			for (int e = 0; e < kPer; ++e)
 			{
+				// the 32 positions of a warp lie in one block (B >= 512): one cursor atomic per side per warp
 				const int p = tid + e * kBottomThreads;
 				v[e] = p < P2 ? s.comp[p] : ~0ull;
 				dst[e] = 0xffffffffu;
-				if (v[e] != ~0ull)
+				const bool valid = v[e] != ~0ull;
+				const int q = (p < P2 ? p : P2 - 1) >> logB;
+				const SegSel st = s.sel[q];
+				const u32 key = (u32)(v[e] >> 13), need = st.krem + 1;
+				const bool isl = valid && key < st.prefix, isr = valid && key > st.prefix, ise = valid && key == st.prefix;
+				const u32 bl = __ballot_sync(0xffffffffu, isl), br = __ballot_sync(0xffffffffu, isr), be = __ballot_sync(0xffffffffu, ise);
+				u32 *c = s.cur + 5 * q;
+				const bool split_ties = st.eq != need;
+				u32 ol = 0, orr = 0, oe = 0;
+				if (lane == 0)
 				{
-					const int q = p >> logB;
-					const SegSel st = s.sel[q];
-					const u32 key = (u32)(v[e] >> 13), need = st.krem + 1;
-					u32 *c = s.cur + 5 * q;
-					if (key < st.prefix) dst[e] = q * B + atomicAdd(&c[0], 1u);
-					else if (key > st.prefix)
-					{
-						dst[e] = q * B + (B >> 1) + atomicAdd(&c[1], 1u);
-						atomicMin(&c[4], key);
-					}
-					else if (st.eq == need) dst[e] = q * B + st.less + atomicAdd(&c[2], 1u);
-					else tl[q * B + atomicAdd(&c[3], 1u)] = (u16)((u32)v[e] & kSlotMask); // ranked below
+					if (bl) ol = atomicAdd(&c[0], (u32)__popc(bl));
+					if (br) orr = atomicAdd(&c[1], (u32)__popc(br));
+					if (be) oe = atomicAdd(split_ties ? &c[3] : &c[2], (u32)__popc(be));
 				}
+				ol = __shfl_sync(0xffffffffu, ol, 0); orr = __shfl_sync(0xffffffffu, orr, 0); oe = __shfl_sync(0xffffffffu, oe, 0);
+				const u32 lt_mask = (1u << lane) - 1u;
+				const u32 rmin = __reduce_min_sync(0xffffffffu, isr ? key : 0xffffffffu);
+				if (lane == 0 && br) atomicMin(&c[4], rmin);
+				if (isl) dst[e] = q * B + ol + __popc(bl & lt_mask);
+				else if (isr) dst[e] = q * B + (B >> 1) + orr + __popc(br & lt_mask);
+				else if (ise && !split_ties) dst[e] = q * B + st.less + oe + __popc(be & lt_mask);
+				else if (ise) tl[q * B + oe + __popc(be & lt_mask)] = (u16)((u32)v[e] & kSlotMask); // ranked below
 			}
 			__syncthreads();
 			for (int p = tid; p < P2; p += kBottomThreads) s.comp[p] = ~0ull;
@@ -756,13 +787,14 @@ int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L)
 	NBCO_TRY(t.hist.reserve(4 * (size_t)kBins0 * nseg));
 	NBCO_TRY(t.sel.reserve(sizeof(SegSel) * nseg)); NBCO_TRY(t.cur.reserve(sizeof(SegCur) * nseg));
 	NBCO_TRY(t.bbox.reserve(64));
+	if (t.lt > 0) NBCO_TRY(t.soa.reserve(12 * (size_t)n));
 	return NBCO_OK;
 }
 
 void kd_release(KdTree &t)
 {
 	DevBuf *all[] = {&t.lbound, &t.rbound, &t.size2, &t.splitdim, &t.chain, &t.keys, &t.idxA, &t.idxB, &t.tie,
-	                 &t.hist, &t.sel, &t.cur, &t.spos, &t.perm, &t.bbox};
+	                 &t.hist, &t.sel, &t.cur, &t.spos, &t.perm, &t.bbox, &t.soa};
 	for (DevBuf *b : all) b->release();
 }
 
@@ -783,8 +815,13 @@ int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos)
 	SegCur *cur = t.cur.as<SegCur>();
 	u32 *ibuf[2] = {t.idxA.as<u32>(), t.idxB.as<u32>()};
 	const int ltop = t.lt; // levels [0, ltop) are partitioned globally
+	float *soa = t.soa.as<float>();
 	if (ltop > 0)
+	{
 		NBCO_CUDA(cudaMemsetAsync(hist, 0, 4 * (size_t)kBins0 * ((size_t)1 << (ltop - 1)), st));
+		to_soa_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(pos, soa, n);
+		++ctx->launches;
+	}
 	const u32 *iin = nullptr; // level 0 reads the identity
 	for (int l = 0; l < ltop; ++l)
 	{
@@ -793,7 +830,7 @@ int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos)
 		const int tps = (int)((maxseg + kSelTile - 1) / kSelTile);
 		const int tiles = nseg * tps;
 		u32 *iout = ibuf[l & 1];
-		keygen_hist_kernel<<<tiles, kSelThreads, 0, st>>>(pos, g.splitdim, iin, keys, hist, n, l, tps);
+		keygen_hist_kernel<<<tiles, kSelThreads, 0, st>>>(soa, g.splitdim, iin, keys, hist, n, l, tps);
 		sel_pick_kernel<0><<<nseg, 256, 0, st>>>(sel, cur, hist, n, l);
 		sel_hist_kernel<1><<<tiles, kSelThreads, 0, st>>>(keys, sel, hist, n, l, tps);
 		sel_pick_kernel<1><<<nseg, 256, 0, st>>>(sel, cur, hist, n, l);

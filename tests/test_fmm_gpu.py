@@ -227,7 +227,7 @@ def test_fmm_sharded_evaluation_tiles_the_single_rank_result(world):
         pu |= set(map(tuple, P)); mu |= set(map(tuple, M))
     assert pu == set(map(tuple, P1)) and mu == set(map(tuple, M1))
     m, mx = mean_rel_err(out, full)
-    assert m < 1e-6 and mx < 1e-5
+    assert m < 1e-6 and mx < 3e-5   # two GPU results, each with its own fp32 atomic-add order
 
 
 def test_sharded_leapfrog_driver_single_rank_matches_integrate():
