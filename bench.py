@@ -202,6 +202,9 @@ def run_ours(args):
         te = float(t.item())
     e2e_value = n * e2e_steps / te
 
+    # secondary metric (BASELINE config 3): O(N^2) direct sum, targets sharded over the ranks
+    direct = bench_direct(nb, torch, dist, local, peaks, rank, world) if args.direct else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -244,34 +247,54 @@ def run_ours(args):
                 "steps": e2e_steps},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    if args.direct and world == 1:
-        out["direct_sum"] = bench_direct(nb, torch, local, peaks)
+    if direct is not None:
+        out["direct_sum"] = direct
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_direct(nb, torch, local, peaks, n=1 << 20):
-    """secondary metric of BASELINE.json: O(N^2) direct sum, FP32-FMA roofline (18 flop / interaction)"""
+def bench_direct(nb, torch, dist, local, peaks, rank, world, n=1 << 20):
+    """secondary metric of BASELINE.json: O(N^2) direct sum, FP32-FMA roofline (18 flop / interaction).
+    Multi-GPU: every rank holds all sources and computes its own target shard (nbco_shard_range);
+    the shards are all-gathered (coulomb_oscillators_b200/parallel.py); time = max over ranks."""
+    from coulomb_oscillators_b200.parallel import all_gather_shards
     state = nb.init_ga(n)
     pos = torch.from_numpy(state[0].copy()).cuda()
     acc = torch.empty_like(pos)
     par = torch.from_numpy(nb.default_param(n)).cuda()
-    ctx = nb.Context(device=local)
+    ctx = nb.Context(device=local, rank=rank, world=world)
     st = torch.cuda.ExternalStream(ctx.stream)
-    ctx.force_direct3(pos.data_ptr(), acc.data_ptr(), n, par.data_ptr())
+    lo, hi = nb.shard_range(n, rank, world)
+
+    def once():
+        ctx.force_direct3(pos.data_ptr(), acc.data_ptr(), n, par.data_ptr())
+        if world > 1:
+            full = all_gather_shards(acc[lo:hi].contiguous(), n)
+            torch.cuda.current_stream().synchronize()
+            return full
+        return acc
+
+    once()
     best = 1e30
     for _ in range(2):
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
-        ctx.force_direct3(pos.data_ptr(), acc.data_ptr(), n, par.data_ptr())
+        once()
         e1.record(st)
         e1.synchronize()
-        best = min(best, e0.elapsed_time(e1))
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        best = min(best, ms)
     inter = n * n / (best * 1e-3)
     sms = torch.cuda.get_device_properties(local).multi_processor_count
-    peak = 2 * sms * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
-    return {"n": n, "ms": best, "Ginteractions_per_s": inter / 1e9,
+    peak = world * 2 * sms * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    return {"n": n, "n_gpus": world, "ms": best, "Ginteractions_per_s": inter / 1e9,
             "roofline": {"bound": "fp32_fma", "achieved": inter * 18 / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": inter * 18 / 1e12 / peak, "flop_per_interaction": 18}}
 

@@ -154,8 +154,8 @@ direct3_scalar_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 }
 
 // Packed FP32x2 variant: targets are processed in pairs (IPT even).
-template <int IPT>
-__global__ void __launch_bounds__(kBlock)
+template <int IPT, int BLOCK = kBlock>
+__global__ void __launch_bounds__(BLOCK)
 direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_begin, int64_t i_end,
                       float *__restrict__ acc, const float *__restrict__ param, float eps2)
 {
@@ -165,14 +165,14 @@ direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 	__shared__ float4 tile_xy[kTileJ];
 	__shared__ float2 tile_z[kTileJ];
 	const int tid = threadIdx.x;
-	const int64_t i0 = i_begin + (int64_t)blockIdx.x * (kBlock * IPT) + tid;
+	const int64_t i0 = i_begin + (int64_t)blockIdx.x * (BLOCK * IPT) + tid;
 
 	f32x2 xi[NP], yi[NP], zi[NP];
 	Kahan3 sum[IPT];
 #pragma unroll
 	for (int k = 0; k < NP; ++k)
 	{
-		int64_t ia = i0 + (int64_t)(2*k) * kBlock, ib = ia + kBlock;
+		int64_t ia = i0 + (int64_t)(2*k) * BLOCK, ib = ia + BLOCK;
 		float4 qa = src[ia < i_end ? ia : i_begin];
 		float4 qb = src[ib < i_end ? ib : i_begin];
 		xi[k] = pack2(qa.x, qb.x); yi[k] = pack2(qa.y, qb.y); zi[k] = pack2(qa.z, qb.z);
@@ -183,7 +183,7 @@ direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 	{
 		int cnt = (int)((n_src - base < kTileJ) ? (n_src - base) : kTileJ);
 		__syncthreads();
-		for (int j = tid; j < cnt; j += kBlock)
+		for (int j = tid; j < cnt; j += BLOCK)
 		{
 			float4 s = src[base + j];
 			tile_xy[j] = make_float4(s.x, s.x, s.y, s.y);
@@ -230,7 +230,7 @@ direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 #pragma unroll
 	for (int k = 0; k < IPT; ++k)
 	{
-		int64_t i = i0 + (int64_t)k * kBlock;
+		int64_t i = i0 + (int64_t)k * BLOCK;
 		if (i < i_end)
 		{
 			acc[3*i]   = scale * sum[k].sx;
@@ -315,6 +315,13 @@ int direct3_launch(nbco_ctx *ctx, const float *d_pos, float *d_acc, int64_t n, c
 		case 3: LAUNCH(direct3_scalar_kernel, 4); break;
 		case 4: LAUNCH(direct3_packed_kernel, 8); break;
 		case 5: LAUNCH(direct3_packed_kernel, 2); break;
+		case 6:
+		{
+			int64_t blocks = (cnt + 256 * 4 - 1) / (256 * 4);
+			direct3_packed_kernel<4, 256><<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, n, ib, ie, d_acc, d_param, eps2);
+			break;
+		}
+		case 7: LAUNCH(direct3_packed_kernel, 6); break;
 		default: LAUNCH(direct3_packed_kernel, 4); break; // measured fastest on B200 (profiles/)
 	}
 #undef LAUNCH

@@ -25,6 +25,7 @@
 //  * operators are compile-time unrolled templates (fmm_ops.cuh), one instantiation per order.
 
 #include "fmm3_common.cuh"
+#include <cooperative_groups.h>
 
 namespace nbco {
 
@@ -143,10 +144,8 @@ __device__ __forceinline__ int expand_pair(int kind, int2 np, int2 *out)
 // level-synchronous round.  Appends are aggregated per CTA: the three output counters (p2p list, m2l
 // list, next frontier) receive ONE atomic each per 256 classified pairs -- per-warp atomics on the same
 // three addresses serialise in L2 and dominated the big rounds (profiles/r01_notes.md).
-__global__ void __launch_bounds__(256) traverse_round_kernel(TravArgs a, int round)
+__device__ __forceinline__ void traverse_round(const TravArgs &a, int round, u32 (*wtot)[3], u32 *base)
 {
-	__shared__ u32 wtot[8][3];
-	__shared__ u32 base[3];
 	u32 *cin = a.cnt + 2 + round % 3, *cout = a.cnt + 2 + (round + 1) % 3, *cnext = a.cnt + 2 + (round + 2) % 3;
 	if (blockIdx.x == 0 && threadIdx.x == 0) *cnext = 0; // nobody touches it during this round
 	const u32 nin = min(*cin, a.cap_front);
@@ -191,45 +190,27 @@ __global__ void __launch_bounds__(256) traverse_round_kernel(TravArgs a, int rou
 	}
 }
 
-// depth-first completion: every lane takes pairs of the last frontier from a global counter and
-// walks their subtrees with a private stack (<= 4L+3 entries); no more launches, no frontier traffic
-constexpr int kDfsStack = 112;
-
-__global__ void __launch_bounds__(128) traverse_dfs_kernel(TravArgs a, int round)
+__global__ void __launch_bounds__(256) traverse_round_kernel(TravArgs a, int round)
 {
-	const u32 nin = min(a.cnt[2 + round % 3], a.cap_front);
-	const int lane = threadIdx.x & 31;
-	const u32 lt_mask = (1u << lane) - 1u;
-	int2 stack[kDfsStack];
-	int top = 0;
-	while (true)
+	__shared__ u32 wtot[8][3];
+	__shared__ u32 base[3];
+	traverse_round(a, round, wtot, base);
+}
+
+// all rounds in one cooperative launch: a grid-wide barrier replaces ~2L kernel boundaries (most rounds
+// classify a few thousand pairs and are dominated by launch and ramp-up time)
+__global__ void __launch_bounds__(256) traverse_all_kernel(TravArgs a, int2 *fa, int2 *fb, int max_rounds)
+{
+	__shared__ u32 wtot[8][3];
+	__shared__ u32 base[3];
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	for (int r = 0; r < max_rounds; ++r)
 	{
-		const bool want = top == 0;
-		const u32 wmask = __ballot_sync(0xffffffffu, want);
-		if (wmask)
-		{
-			u32 base = 0;
-			const int leader = __ffs(wmask) - 1;
-			if (lane == leader) base = atomicAdd(a.cnt + 6, (u32)__popc(wmask));
-			base = __shfl_sync(0xffffffffu, base, leader);
-			const u32 idx = base + __popc(wmask & lt_mask);
-			if (want && idx < nin) stack[top++] = a.front_in[idx];
-		}
-		const bool has = top > 0;
-		if (!__any_sync(0xffffffffu, has)) break;
-		int kind = 0, flags = 0;
-		int2 np = make_int2(0, 0);
-		if (has) { np = stack[--top]; kind = classify_pair(a, np, flags); }
-		const int2 tagged = make_int2(np.x | (flags << kFlagShift), np.y);
-		u32 s1 = warp_append(a.cnt + 0, kind == 1);
-		if (kind == 1 && s1 < a.cap_p2p) a.p2p[s1] = tagged;
-		u32 s2 = warp_append(a.cnt + 1, kind == 2);
-		if (kind == 2 && s2 < a.cap_m2l) a.m2l[s2] = tagged;
-		if (kind >= 3)
-		{
-			if (top + 3 <= kDfsStack) top += expand_pair(kind, np, stack + top);
-			else a.cnt[5] = 1u;
-		}
+		a.front_in = (r & 1) ? fb : fa;
+		a.front_out = (r & 1) ? fa : fb;
+		if (*(volatile u32 *)(a.cnt + 2 + r % 3) == 0) break; // uniform: the counter was final before the last barrier
+		traverse_round(a, r, wtot, base);
+		grid.sync();
 	}
 }
 
@@ -252,30 +233,29 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 	return y;
 }
 
-// a group of G lanes handles one leaf pair (both directions) or one leaf against itself
-template <int G, bool SELF>
+// a group of G lanes handles one leaf pair, both directions (the intra-leaf part lives in the L2P kernel)
+template <int G>
 __global__ void __launch_bounds__(256)
 p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap, const float *__restrict__ spos,
-           float *__restrict__ acc, int64_t n, int L, float eps2, int leaf_lo, int leaf_hi)
+           float *__restrict__ acc, int64_t n, int L, float eps2)
 {
 	const int lane = threadIdx.x & (G - 1);
 	const int groups = (gridDim.x * blockDim.x) / G;
 	const int beg = kd_beg(L);
-	const u32 npairs = SELF ? (u32)(leaf_hi - leaf_lo) : min(*count, cap);
+	const u32 npairs = min(*count, cap);
 	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
 	const u32 nwork = ((npairs + (32 / G) - 1) / (32 / G)) * (32 / G); // keep whole warps in the loop
 	for (u32 w = (blockIdx.x * blockDim.x + threadIdx.x) / G; w < nwork; w += groups)
 	{
 		if (w >= npairs) continue;
-		int l1, l2, flags = 3;
-		if (SELF) { l1 = l2 = leaf_lo + (int)w; }
-		else { int2 np = list[w]; flags = (np.x >> kFlagShift) & 3; l1 = (np.x & kNodeMask) - beg; l2 = np.y - beg; }
+		const int2 np = list[w];
+		const int flags = (np.x >> kFlagShift) & 3, l1 = (np.x & kNodeMask) - beg, l2 = np.y - beg;
 		const int64_t i1 = seg_start(n, l1, L), i2 = seg_start(n, l2, L);
 		const int m1 = (int)(seg_start(n, l1 + 1, L) - i1), m2 = (int)(seg_start(n, l2 + 1, L) - i2);
 #pragma unroll 1
-		for (int dir = 0; dir < (SELF ? 1 : 2); ++dir)
+		for (int dir = 0; dir < 2; ++dir)
 		{
-			if (!SELF && !((flags >> dir) & 1)) continue; // the other rank owns these targets
+			if (!((flags >> dir) & 1)) continue; // another rank owns these targets
 			const int64_t ti = dir ? i2 : i1, si = dir ? i1 : i2;
 			const int tm = dir ? m2 : m1, sm = dir ? m1 : m2;
 			for (int h0 = 0; h0 < tm; h0 += G)
@@ -338,6 +318,7 @@ struct FmmPlan
 	bool ev_ok = false, ev_valid = false;
 	double tot_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	int64_t tot_evals = 0, tot_rebuilds = 0;
+	int coop_blocks = -1; // grid of the cooperative traversal kernel (0 = not available)
 };
 
 static int plan_levels(int64_t n, int order, float dens, int max_level)
@@ -437,23 +418,36 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	// multi-GPU: rank r of 2^g owns the subtree of node (g, r): a contiguous range of leaves and particles
 	int g = 0;
 	while ((1 << g) < c.world) ++g;
-	const int leaf_lo = c.rank << (L - g), leaf_hi = (c.rank + 1) << (L - g);
 	a.sh_lo = seg_start(n, c.rank, g); a.sh_hi = seg_start(n, c.rank + 1, g);
 	traverse_init_kernel<<<1, 32, 0, st>>>(p.frontA.as<int2>(), a.cnt); LAUNCHED(ctx);
-	// breadth first while the frontier is small, then one depth-first kernel finishes every subtree
-	static int env_rounds = -2;
-	if (env_rounds == -2) { const char *e = getenv("NBCO_TRAV_ROUNDS"); env_rounds = e ? atoi(e) : -1; }
-	// measured on B200 (profiles/r01_notes.md): the depth-first tail is 2-25x slower than breadth-first rounds
-	// (private stacks in local memory, divergent subtrees), so by default every round is breadth first
-	const int rounds = env_rounds >= 0 ? std::min(env_rounds, 2 * L + 2) : 2 * L + 2;
-	for (int r = 0; r <= rounds; ++r)
+	// breadth first: a pair is split at most once per round, 2L + 2 rounds always suffice.  (A depth-first
+	// tail with private stacks was measured 2-25x slower on B200, profiles/r01_notes.md.)
+	const int rounds = 2 * L + 2;
+	if (p.coop_blocks < 0)
 	{
-		a.front_in = (r & 1) ? p.frontB.as<int2>() : p.frontA.as<int2>();
-		a.front_out = (r & 1) ? p.frontA.as<int2>() : p.frontB.as<int2>();
-		if (r < rounds) traverse_round_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, r);
-		else traverse_dfs_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(a, r);
+		int coop = 0, per_sm = 0;
+		cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->cfg.device);
+		if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, traverse_all_kernel, 256, 0) == cudaSuccess && per_sm > 0)
+			p.coop_blocks = ctx->sm_count * std::min(per_sm, 4);
+		else
+			p.coop_blocks = 0;
+	}
+	if (p.coop_blocks > 0)
+	{
+		int2 *fa = p.frontA.as<int2>(), *fb = p.frontB.as<int2>();
+		int max_rounds = rounds;
+		void *args[] = {&a, &fa, &fb, &max_rounds};
+		NBCO_CUDA(cudaLaunchCooperativeKernel((void *)traverse_all_kernel, dim3(p.coop_blocks), dim3(256), args, 0, st));
 		LAUNCHED(ctx);
 	}
+	else
+		for (int r = 0; r < rounds; ++r)
+		{
+			a.front_in = (r & 1) ? p.frontB.as<int2>() : p.frontA.as<int2>();
+			a.front_out = (r & 1) ? p.frontA.as<int2>() : p.frontB.as<int2>();
+			traverse_round_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, r);
+			LAUNCHED(ctx);
+		}
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_P2P], st));
 	float *accn = p.accn.as<float>();
@@ -463,7 +457,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 		const int blocks = ctx->sm_count * 8;
 #define P2P_LAUNCH(G)                                                                                              \
 		do {                                                                                                       \
-			p2p_kernel<G, false><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2, leaf_lo, leaf_hi); \
+			p2p_kernel<G><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2); \
 		} while (0)
 		if (p.mlt_max <= 4) P2P_LAUNCH(4);
 		else if (p.mlt_max <= 8) P2P_LAUNCH(8);

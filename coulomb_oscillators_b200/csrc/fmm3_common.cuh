@@ -107,6 +107,15 @@ int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L);
 int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos);
 void kd_release(KdTree &t);
 
+// leaf (or node of level l) that owns sorted position j: floor(2^l j / n) (:162-164) without a 64-bit
+// division: multiply by magic = floor(2^64 / n) and correct by at most one step
+__device__ __forceinline__ int owner_of(int64_t j, int64_t n, int l, unsigned long long magic)
+{
+	int q = (int)__umul64hi(((unsigned long long)j) << l, magic);
+	if (seg_start(n, q + 1, l) <= j) ++q;
+	return q;
+}
+
 // intra-leaf near field of one particle (fmm_p2p3_self_kdtree, :1048-1120): the other particles of its
 // leaf, read through L1 (a leaf is 1-2 cache lines); i = j contributes exactly 0
 __device__ __forceinline__ void self_p2p(float *f, const float *__restrict__ spos, int64_t j, int leaf,

@@ -205,11 +205,12 @@ l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__
 	float k3[3] = {1.f, 1.f, 1.f};
 	if (fuse_elastic && param) { k3[0] = param[3]; k3[1] = param[4]; k3[2] = param[5]; }
 	const int beg = kd_beg(L);
+	const unsigned long long magic = ~0ull / (unsigned long long)n; // floor((2^64 - 1) / n) <= 2^64 / n: never overshoots
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	for (int64_t j = j_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < j_hi; j += stride)
 	{
 		// leaf of sorted position j: floor(2^L j / n) (:162-164)
-		const int leaf = (int)((((unsigned long long)j) << L) / (unsigned long long)n);
+		const int leaf = owner_of(j, n, L, magic);
 		const float4 c = t.center[beg + leaf];
 		float Lq[pad4<trl_off(P + 1)>()], S[sym_off(P + 1)];
 		load_tuple<trl_off(P + 1)>(Lq, t.local + (int64_t)(beg + leaf) * t.sL);

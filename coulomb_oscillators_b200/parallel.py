@@ -38,6 +38,16 @@ def sharded_direct3(compute_shard, pos, n, group=None):
     return all_gather_shards(acc[b:e].contiguous(), n, group)
 
 
+def next_eval_rebuilds(ctx):
+    """True when the next FMM evaluation of this context rebuilds the kd-tree (counter % tree_steps == 0,
+    fmm_cart3_kdtree.cuh:1619); a context that has not evaluated yet always builds."""
+    from ._lib import NbcoError
+    try:
+        return ctx.fmm_info().counter % ctx.cfg.tree_steps == 0
+    except NbcoError:
+        return True
+
+
 def fmm_leapfrog_sharded(ctx, buf, n, d_param, dt, nsteps, group=None):
     """Leapfrog steps of coulombOscillatorFMMKD3 over `world` GPUs (one process per GPU).
 
@@ -84,7 +94,7 @@ def fmm_leapfrog_sharded(ctx, buf, n, d_param, dt, nsteps, group=None):
         ctx.step(p0 + 4 * (3 * n + 3 * b), p0 + 4 * (6 * n + 3 * b), half, cnt)   # v += a dt/2   (own range)
         ctx.step(p0 + 4 * (3 * b), p0 + 4 * (3 * n + 3 * b), dtf, cnt)            # x += v dt
         gather(pos, b, e)
-        if ctx.fmm_info().counter % ctx.cfg.tree_steps == 0:
+        if next_eval_rebuilds(ctx):
             gather(vel, b, e)                                                     # the rebuild permutes everything
         ctx.coulomb_fmm3_kd(p0, p0 + 4 * 6 * n, n, d_param)                       # a = f(x)     (own range written)
         ctx.step(p0 + 4 * (3 * n + 3 * b), p0 + 4 * (6 * n + 3 * b), half, cnt)   # v += a dt/2

@@ -1,0 +1,83 @@
+"""The nbco3 command line (C++ host code over the C ABI): option surface, file naming, snapshot
+format, and agreement with the reference's own CLI run (`nbco3 -cpu`, through oracle/_ref)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import coulomb_oscillators_b200 as nb
+from refs import REF_SO, Ref
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "coulomb_oscillators_b200", "nbco3")
+
+
+def run(args, cwd):
+    return subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True, timeout=300)
+
+
+def test_cli_snapshots_and_format(tmp_path):
+    out = tmp_path / "out"
+    out.mkdir()
+    n = 5000
+    r = run(["-n", str(n), "-iters", "4", "-steps", "2", "-o", str(out)], tmp_path)
+    assert r.returncode == 0, r.stderr
+    names = sorted(os.listdir(out))
+    # "-iters 4" runs 5 iterations (main3.cu:232,357); snapshots after iterations 0, 2, 4 (:841-858)
+    assert names == ["args.txt", "out0_0.000500.bin", "out2_0.000500.bin", "out4_0.000500.bin"]
+    for f in names[1:]:
+        assert os.path.getsize(out / f) == 24 * n                # all positions then all velocities, fp32
+    assert open(out / "args.txt").read().split()[1:] == ["-n", str(n), "-iters", "4", "-steps", "2", "-o", str(out)]
+    # resume: a snapshot is a valid [input] (main3.cu:629-652)
+    out2 = tmp_path / "out2"
+    out2.mkdir()
+    r = run(["-iters", "0", "-steps", "1", "-o", str(out2), str(out / "out0_0.000500.bin")], tmp_path)
+    assert r.returncode == 0 and os.path.getsize(out2 / "out0_0.000500.bin") == 24 * n
+
+
+def test_cli_errors(tmp_path):
+    assert run(["-bogus"], tmp_path).returncode != 0
+    assert "unrecognised option" in run(["-bogus"], tmp_path).stderr
+    assert run(["-integ", "nope"], tmp_path).returncode != 0
+    r = run(["-n", "1000", "-iters", "0", "-o", str(tmp_path / "missing")], tmp_path)
+    assert r.returncode != 0 and "Create it if not" in r.stderr
+    assert "no CPU path" in run(["-cpu"], tmp_path).stderr
+    assert run(["-h"], tmp_path).returncode == 0
+
+
+def test_cli_integrator_spellings(tmp_path):
+    out = tmp_path / "o"
+    out.mkdir()
+    for spelling in ("-fr", "fr", "-pefrl", "eu"):                 # the reference only accepts the dashed form (:389-395)
+        assert run(["-n", "2000", "-iters", "0", "-steps", "1", "-integ", spelling, "-o", str(out)], tmp_path).returncode == 0
+
+
+def test_cli_test_mode_prints_reference_error_table(tmp_path):
+    r = run(["-test", "-n", "8192"], tmp_path)
+    assert r.returncode == 0, r.stderr
+    errs = [float(l.split(":")[-1]) for l in r.stdout.splitlines() if "Relative error" in l]
+    want = [0.2315, 0.1070, 0.0595, 0.0299, 0.0153, 0.00934]      # `nbco3 -cpu -test -n 8192`, SURVEY.md section 6
+    assert len(errs) == 6
+    for g, w in zip(errs, want):
+        assert abs(g - w) <= 0.35 * w   # the CLI runs the GPU traversal order (MAC first): same class, different lists
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not shipped")
+def test_cli_first_snapshot_matches_reference_cli(tmp_path):
+    """one iteration of both programs from the same seed: the snapshot after step 0"""
+    n = 4096
+    ours, theirs = tmp_path / "a", tmp_path / "b"
+    ours.mkdir(); theirs.mkdir()
+    assert run(["-n", str(n), "-iters", "0", "-steps", "1", "-o", str(ours)], tmp_path).returncode == 0
+    code = ("import ctypes as C, sys; L = C.CDLL(sys.argv[1]); a = [b'nbco3', b'-cpu', b'-n', sys.argv[2].encode(), b'-iters', b'0', "
+            "b'-steps', b'1', b'-o', sys.argv[3].encode()]; arr = (C.c_char_p * len(a))(*a); sys.exit(L.ref_cli(len(a), arr))")
+    r = subprocess.run(["python", "-c", code, REF_SO, str(n), str(theirs)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    a = np.fromfile(ours / "out0_0.000500.bin", np.float32).reshape(2, n, 3)
+    b = np.fromfile(theirs / "out0_0.000500.bin", np.float32).reshape(2, n, 3)
+    # both files are in tree order of the same tree (first build from the same initial conditions)
+    assert np.abs(a[0] - b[0]).max() <= 1e-6 * np.abs(b[0]).max()
+    assert np.abs(a[1] - b[1]).max() <= 1e-4 * np.abs(b[1]).max()
