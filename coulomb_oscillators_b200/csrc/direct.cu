@@ -154,7 +154,7 @@ direct3_scalar_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 }
 
 // Packed FP32x2 variant: targets are processed in pairs (IPT even).
-template <int IPT, int BLOCK = kBlock>
+template <int IPT, int BLOCK = kBlock, int UNROLL = 4>
 __global__ void __launch_bounds__(BLOCK)
 direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_begin, int64_t i_end,
                       float *__restrict__ acc, const float *__restrict__ param, float eps2)
@@ -195,7 +195,7 @@ direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 #pragma unroll
 		for (int k = 0; k < NP; ++k) { ax[k] = 0ull; ay[k] = 0ull; az[k] = 0ull; }
 
-#pragma unroll 4
+#pragma unroll UNROLL
 		for (int j = 0; j < cnt; ++j)
 		{
 			const ulonglong2 sxy = *reinterpret_cast<const ulonglong2 *>(&tile_xy[j]);
@@ -322,7 +322,20 @@ int direct3_launch(nbco_ctx *ctx, const float *d_pos, float *d_acc, int64_t n, c
 			break;
 		}
 		case 7: LAUNCH(direct3_packed_kernel, 6); break;
-		default: LAUNCH(direct3_packed_kernel, 4); break; // measured fastest on B200 (profiles/)
+#define LAUNCH_P(IPT, BLK, UNR)                                                                          \
+		{                                                                                                \
+			int64_t blocks = (cnt + (int64_t)BLK * IPT - 1) / ((int64_t)BLK * IPT);                      \
+			direct3_packed_kernel<IPT, BLK, UNR><<<(unsigned)blocks, BLK, 0, ctx->stream>>>(src, n, ib, ie, d_acc, d_param, eps2); \
+			break;                                                                                       \
+		}
+		case 8: LAUNCH_P(4, 256, 8)
+		case 9: LAUNCH_P(4, 512, 4)
+		case 10: LAUNCH_P(4, 256, 2)
+		case 11: LAUNCH_P(2, 256, 8)
+		case 12: LAUNCH_P(4, 128, 8)
+		case 13: LAUNCH(direct3_packed_kernel, 4); break;
+		default: LAUNCH_P(4, 256, 4) // measured fastest on B200 (profiles/r01_notes.md)
+#undef LAUNCH_P
 	}
 #undef LAUNCH
 	++ctx->launches;

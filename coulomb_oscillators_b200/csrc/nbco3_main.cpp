@@ -48,6 +48,8 @@ const char *kHelp =
 	"  -i <x>                 density inhomogeneity factor for the tree depth. Default is 1\n"
 	"  -maxlevel <L>          force the tree depth. Default is automatic\n"
 	"  -ncoll                 skip the near field (P2P)\n"
+	"  -tree-steps <k>        (extension) rebuild the kd-tree every k force evaluations. Default is 8\n"
+	"  -m2l-first <0|1>       (extension) 1: MAC before leaf test (reference GPU order, default), 0: reference CPU order\n"
 	"  -accuracy <v>          search (p, r) for a mean relative error below v, then run\n"
 	"  -test                  timing and error against the direct sum for p = 1..6 on a uniform cube\n"
 	"  -test2                 error against the direct sum over tree_steps+1 Euler steps\n"
@@ -108,6 +110,9 @@ int main(int argc, const char **argv)
 		else if (a == "-i") { if (!need(i, 1)) return fail("Error: no inhomogeneity specified."); cfg.dens_inhom = (float)atof(argv[++i]); }
 		else if (a == "-maxlevel") { if (!need(i, 1)) return fail("Error: no level specified."); cfg.max_level = atoi(argv[++i]); }
 		else if (a == "-ncoll") cfg.coll = 0;
+		// extensions (not in the reference CLI): its global tree_steps (constants.cuh:45) and the traversal order
+		else if (a == "-tree-steps") { if (!need(i, 1)) return fail("Error: no tree_steps specified."); cfg.tree_steps = atoi(argv[++i]); }
+		else if (a == "-m2l-first") { if (!need(i, 1)) return fail("Error: no value specified."); cfg.m2l_first = atoi(argv[++i]); }
 		else if (a == "-accuracy") { if (!need(i, 1)) return fail("Error: no accuracy specified."); accuracy = (float)atof(argv[++i]); b_accuracy = true; }
 		else if (a == "-test") test = true;
 		else if (a == "-test2") test2 = true;

@@ -71,13 +71,18 @@ def test_cli_first_snapshot_matches_reference_cli(tmp_path):
     n = 4096
     ours, theirs = tmp_path / "a", tmp_path / "b"
     ours.mkdir(); theirs.mkdir()
-    assert run(["-n", str(n), "-iters", "0", "-steps", "1", "-o", str(ours)], tmp_path).returncode == 0
+    # the reference CPU path rebuilds the tree at every evaluation and tests leaves before the MAC
+    assert run(["-n", str(n), "-iters", "0", "-steps", "1", "-tree-steps", "1", "-m2l-first", "0", "-o", str(ours)], tmp_path).returncode == 0
     code = ("import ctypes as C, sys; L = C.CDLL(sys.argv[1]); a = [b'nbco3', b'-cpu', b'-n', sys.argv[2].encode(), b'-iters', b'0', "
             "b'-steps', b'1', b'-o', sys.argv[3].encode()]; arr = (C.c_char_p * len(a))(*a); sys.exit(L.ref_cli(len(a), arr))")
     r = subprocess.run(["python", "-c", code, REF_SO, str(n), str(theirs)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     a = np.fromfile(ours / "out0_0.000500.bin", np.float32).reshape(2, n, 3)
     b = np.fromfile(theirs / "out0_0.000500.bin", np.float32).reshape(2, n, 3)
-    # both files are in tree order of the same tree (first build from the same initial conditions)
-    assert np.abs(a[0] - b[0]).max() <= 1e-6 * np.abs(b[0]).max()
-    assert np.abs(a[1] - b[1]).max() <= 1e-4 * np.abs(b[1]).max()
+    # Both files are in tree order, but not of the same tree: the reference CPU path rebuilds (and re-permutes)
+    # at every evaluation, the GPU path every tree_steps.  Match particles by position first.
+    from scipy.spatial import cKDTree
+    dist, j = cKDTree(b[0].astype(np.float64)).query(a[0].astype(np.float64))
+    assert len(np.unique(j)) == n                                   # a bijection
+    assert dist.max() <= 1e-6 * np.abs(b[0]).max()
+    assert np.abs(a[1] - b[1][j]).max() <= 1e-4 * np.abs(b[1]).max()
