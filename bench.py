@@ -89,19 +89,41 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+SINGLE_KERNEL_PHASES = {"kd_bottom": "kd_bottom_kernel", "p2p": "p2p_kernel", "m2l": "m2l_kernel", "l2p": "l2p_kernel"}
+# DRAM bytes per launch from `ncu --set full` captures of this round (profiles/r01_notes.md); None = not captured
+NCU_TRAFFIC = {"kd_bottom": {"n": 1 << 24, "bytes": 1.690451e9 + 421.263616e6}}
+
+
+def kd_top_levels(n, L, cap=8192):
+    """levels partitioned globally before the shared-memory kernel takes over (kdtree.cu: kd_reserve)"""
+    lt = 0
+    while ((n - 1) >> lt) + 1 > cap:
+        lt += 1
+    return min(lt, L - 1)
+
+
 def fmm_bytes_per_eval(n, order, L, p2p_pairs, m2l_pairs):
-    """algorithmic bytes of one FMM evaluation per phase"""
+    """algorithmic bytes of one FMM evaluation per phase.  The survey's
+    rebuild figure (16 L + 52) N is apportioned by level count between the global levels (kd_top), the
+    shared-memory levels (kd_bottom) and the final permutation of pos/vel (permute, 40 N)."""
     Nl, Nn = 1 << L, (1 << (L + 1)) - 1
     SM = 4 * order * (order + 1) * (order + 2) // 6
     SL = 4 * (order + 1) ** 2
+    lt = kd_top_levels(n, L)
     return {
+        "kd_top": (16 * lt + 12) * n,
+        "kd_bottom": 16 * (L - lt) * n,
+        "permute": 40 * n,
         "p2m_m2m": 12 * n + Nl * (12 + SM) + (2 * Nn - Nl) * (16 + SM),
         "traverse": 40 * Nn + 8 * (m2l_pairs + p2p_pairs),
         "m2l": 8 * m2l_pairs + Nn * (12 + SM) + Nn * SL,
         "p2p": 8 * p2p_pairs + 8 * Nl + 24 * n,
-        "l2l_l2p": Nn * (12 + 2 * SL) + Nl * (12 + SL) + 36 * n,
-        "kd_build": (16 * L + 52) * n,
+        "l2l": Nn * (12 + 2 * SL),
+        "l2p": Nl * (12 + SL) + 36 * n,
     }
+
+
+REBUILD_PHASES = ("kd_top", "kd_bottom", "permute")
 
 
 def run_ours(args):
@@ -182,11 +204,21 @@ def run_ours(args):
     def e2e_step():
         if world == 1:
             ctx_e.step_host(nb.LEAPFROG, ev, hnp, n, par, dt, 1)
-        else:  # every rank uploads the state, the ranks step it together, every rank reads it back
-            buf.copy_(hbuf, non_blocking=True)
+        else:
+            # every rank uploads all positions (the tree is replicated) and its own range of vel / acc,
+            # the ranks step together, every rank reads back its own range of pos / vel / acc
+            lo, hi = nb.shard_range(n, rank, world)
+            buf[:3 * n].copy_(hbuf[:3 * n], non_blocking=True)
+            for k in (1, 2):
+                buf[3 * n * k + 3 * lo:3 * n * k + 3 * hi].copy_(hbuf[3 * n * k + 3 * lo:3 * n * k + 3 * hi], non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            fmm_leapfrog_sharded(ctx_e, buf, n, dpar.data_ptr(), dt, 1)
-            hbuf.copy_(buf, non_blocking=True)
+            fmm_leapfrog_sharded(ctx_e, buf, n, dpar.data_ptr(), dt, 1, gather_final=False)
+            for k in (0, 1, 2):
+                hbuf[3 * n * k + 3 * lo:3 * n * k + 3 * hi].copy_(buf[3 * n * k + 3 * lo:3 * n * k + 3 * hi], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            # positions of the other ranks reach the host through their own read-back; here the host copy of
+            # the full position array is refreshed from the device copy the all-gather already left behind
+            hbuf[:3 * n].copy_(buf[:3 * n], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
     e2e_step()   # warm-up (allocations, first rebuild)
@@ -211,22 +243,31 @@ def run_ours(args):
         return
 
     value = n * args.steps / (ms * 1e-3)   # one system of n particles, whatever the number of GPUs
-    # ---- roofline of the dominant phase ----
+    # ---- per-phase times (CUDA events on the context stream, summed over the timed region) ----
     bytes_eval = fmm_bytes_per_eval(n, order, info.levels, info.p2p_pairs, info.m2l_pairs)
     phases = {}
+    total_ms = max(sum(totals.values()), 1e-9)
     for k, tot in totals.items():
-        calls = rebuilds if k == "kd_build" else evals
+        calls = rebuilds if k in REBUILD_PHASES else evals
         if calls == 0:
             continue
         avg_ms = tot / calls
-        phases[k] = {"avg_ms": round(avg_ms, 4), "share": round(tot / max(sum(totals.values()), 1e-9), 4),
+        phases[k] = {"avg_ms": round(avg_ms, 4), "launches": int(calls), "share": round(tot / total_ms, 4),
                      "GBps": round(bytes_eval[k] / (avg_ms * 1e-3) / 1e9, 1) if avg_ms > 0 else None}
-    dom = max(totals, key=lambda k: totals[k])
-    dcalls = rebuilds if dom == "kd_build" else evals
-    achieved = bytes_eval[dom] / (totals[dom] / dcalls * 1e-3) / 1e9
-    step_bytes = sum(v for k, v in bytes_eval.items() if k != "kd_build") + bytes_eval["kd_build"] / 8 + 60 * n
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None, "peak_kind": peak_kind,
+    # ---- roofline of the dominant KERNEL: the single-kernel phase with the largest total time ----
+    dom = max(SINGLE_KERNEL_PHASES, key=lambda k: totals.get(k, 0.0))
+    dcalls = rebuilds if dom in REBUILD_PHASES else evals
+    dom_ms = totals[dom] / max(dcalls, 1)
+    achieved = bytes_eval[dom] / (dom_ms * 1e-3) / 1e9
+    tr = NCU_TRAFFIC.get(dom)
+    step_bytes = sum(v for k, v in bytes_eval.items() if k not in REBUILD_PHASES) \
+        + sum(bytes_eval[k] for k in REBUILD_PHASES) / 8 + 60 * n
+    roofline = {"bound": "hbm", "kernel": SINGLE_KERNEL_PHASES[dom], "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
+                "traffic": tr["bytes"] if tr and tr["n"] == n else None, "peak_kind": peak_kind,
+                "avg_launch_ms": round(dom_ms, 4), "launches": int(dcalls),
+                "algorithmic_bytes_per_launch": int(bytes_eval[dom]),
+                "share_of_step": round(totals[dom] / total_ms, 4),
                 "step_bytes_per_particle": round(step_bytes / n, 1),
                 "step_hbm_frac": round(step_bytes * (args.steps / (ms * 1e-3)) / 1e9 / peaks["hbm_gbs"], 4)}
 
@@ -243,8 +284,9 @@ def run_ours(args):
                    "l2_hygiene": "inputs larger than L2 (state 36 B x N + tree slab)" if 36 * n > 126e6 else "working set may fit L2",
                    "e2e_copies": "every step: H2D [pos|vel|acc] from pinned memory + D2H of the same"},
         "roofline": roofline, "phases": phases, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 36 * n, "d2h_bytes_per_step": 36 * n,
-                "steps": e2e_steps},
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s",
+                "h2d_bytes_per_step": 36 * n if world == 1 else world * 12 * n + 24 * n,
+                "d2h_bytes_per_step": 36 * n if world == 1 else world * 12 * n + 24 * n, "steps": e2e_steps},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if direct is not None:

@@ -300,8 +300,9 @@ p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap
 // =====================================================================================
 //  host side: plan, phases, introspection
 // =====================================================================================
-enum Phase { PH_BUILD = 0, PH_UPWARD, PH_TRAVERSE, PH_P2P, PH_M2L, PH_DOWNWARD, PH_COUNT };
-static const char *kPhaseNames[PH_COUNT] = {"kd_build", "p2m_m2m", "traverse", "p2p", "m2l", "l2l_l2p"};
+enum Phase { PH_KDTOP = 0, PH_KDBOTTOM, PH_PERMUTE, PH_UPWARD, PH_TRAVERSE, PH_P2P, PH_M2L, PH_L2L, PH_L2P, PH_COUNT };
+// single-kernel phases: kd_bottom, p2p, m2l, l2p (their CUDA-event times are kernel launch durations)
+static const char *kPhaseNames[PH_COUNT] = {"kd_top", "kd_bottom", "permute", "p2m_m2m", "traverse", "p2p", "m2l", "l2l", "l2p"};
 
 struct FmmPlan
 {
@@ -316,7 +317,7 @@ struct FmmPlan
 	DevBuf p2p, m2l, frontA, frontB, cnt, mfac;
 	cudaEvent_t ev[PH_COUNT + 1];
 	bool ev_ok = false, ev_valid = false;
-	double tot_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	double tot_ms[PH_COUNT] = {};
 	int64_t tot_evals = 0, tot_rebuilds = 0;
 	int coop_blocks = -1; // grid of the cooperative traversal kernel (0 = not available)
 };
@@ -389,11 +390,17 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	const nbco_config &c = ctx->cfg;
 	TreeData t{p.center.as<float4>(), p.kd.size2.as<float>(), p.mpole.as<float>(), p.local.as<float>(), p.sM, p.sL};
 
-	NBCO_CUDA(cudaEventRecord(p.ev[PH_BUILD], st));
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_KDTOP], st));
 	const float *spos = d_pos; // tree-ordered positions the passes read
-	if (rebuild)
+	if (!rebuild)
 	{
-		NBCO_TRY(kd_build(ctx, p.kd, d_pos));
+		NBCO_CUDA(cudaEventRecord(p.ev[PH_KDBOTTOM], st));
+		NBCO_CUDA(cudaEventRecord(p.ev[PH_PERMUTE], st));
+	}
+	else
+	{
+		NBCO_TRY(kd_build(ctx, p.kd, d_pos, p.ev[PH_KDBOTTOM]));
+		NBCO_CUDA(cudaEventRecord(p.ev[PH_PERMUTE], st));
 		if (c.unsort)
 			spos = p.kd.spos.as<float>();
 		else
@@ -449,9 +456,9 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 			LAUNCHED(ctx);
 		}
 
-	NBCO_CUDA(cudaEventRecord(p.ev[PH_P2P], st));
 	float *accn = p.accn.as<float>();
 	NBCO_CUDA(cudaMemsetAsync(accn, 0, 12 * (size_t)n, st));
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_P2P], st)); // the p2p phase is exactly one kernel
 	if (c.coll)
 	{
 		const int blocks = ctx->sm_count * 8;
@@ -470,8 +477,9 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_M2L], st));
 	ops.m2l(ctx, t, a.m2l, a.cnt + 1, a.cap_m2l, c.eps2);
 
-	NBCO_CUDA(cudaEventRecord(p.ev[PH_DOWNWARD], st));
-	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll);
+	NBCO_CUDA(cudaEventRecord(p.ev[PH_L2L], st));
+	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll,
+	             p.ev[PH_L2P]);
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_COUNT], st));
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;
@@ -656,7 +664,7 @@ int nbco_fmm_phase_totals(nbco_ctx *ctx, const char **names, double *ms, int cap
 	int k = 0;
 	for (; k < PH_COUNT && k < cap; ++k) { names[k] = kPhaseNames[k]; ms[k] = p.tot_ms[k]; }
 	if (h_evals) { h_evals[0] = p.tot_evals; h_evals[1] = p.tot_rebuilds; }
-	if (reset) { for (int i = 0; i < 8; ++i) p.tot_ms[i] = 0; p.tot_evals = p.tot_rebuilds = 0; }
+	if (reset) { for (int i = 0; i < PH_COUNT; ++i) p.tot_ms[i] = 0; p.tot_evals = p.tot_rebuilds = 0; }
 	return k;
 }
 

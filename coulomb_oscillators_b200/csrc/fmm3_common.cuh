@@ -104,7 +104,7 @@ struct KdTree
 	bool bottom_attr = false;
 };
 int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L);
-int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos);
+int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom);
 void kd_release(KdTree &t);
 
 // leaf (or node of level l) that owns sorted position j: floor(2^l j / n) (:162-164) without a 64-bit
@@ -148,7 +148,7 @@ struct OrderOps
 	// rank r of 2^g ranks pushes locals down its own subtree (plus the ancestors of its root) only
 	void (*downward)(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
 	                 const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g,
-	                 float eps2, int coll);
+	                 float eps2, int coll, cudaEvent_t ev_l2p /* recorded between the L2L levels and the L2P kernel */);
 };
 const OrderOps *order_ops(int order);
 

@@ -248,7 +248,7 @@ struct OrderImpl
 		m2l_kernel<P><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2); ++ctx->launches;
 	}
 	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll)
+	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p)
 	{
 		cudaStream_t st = ctx->stream;
 		// locals of levels 0 and 1 stay zero (nothing is ever admissible there); level l+1 pulls from level l >= 1
@@ -261,6 +261,7 @@ struct OrderImpl
 				l2l_level_kernel<P><<<(count + 127) / 128, 128, 0, st>>>(t, l, first, count); ++ctx->launches;
 			}
 		}
+		if (ev_l2p) cudaEventRecord(ev_l2p, st);
 		const int64_t j_lo = seg_start(n, r, g), j_hi = seg_start(n, r + 1, g);
 		l2p_kernel<P><<<grid_for(j_hi - j_lo, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
 		                                                                              param, fuse_elastic, n, L, j_lo, j_hi, eps2, coll);

@@ -345,7 +345,7 @@ struct GenImpl
 		g_m2l_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2, P); ++ctx->launches;
 	}
 	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll)
+	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p)
 	{
 		cudaStream_t st = ctx->stream;
 		if (L >= 2)
@@ -357,6 +357,7 @@ struct GenImpl
 				g_l2l_level_kernel<<<(count + 127) / 128, 128, 0, st>>>(t, l, first, count, P); ++ctx->launches;
 			}
 		}
+		if (ev_l2p) cudaEventRecord(ev_l2p, st);
 		const int64_t j_lo = seg_start(n, r, g), j_hi = seg_start(n, r + 1, g);
 		g_l2p_kernel<<<grid_for(j_hi - j_lo, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
 		                                                                            param, fuse_elastic, n, L, P, j_lo, j_hi, eps2, coll);

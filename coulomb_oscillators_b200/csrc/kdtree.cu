@@ -95,11 +95,19 @@ __device__ __forceinline__ TileRange tile_range(int64_t n, int l, int tps)
 	return r;
 }
 
-// one shared atomic per distinct bin per warp (keys of a segment share their high bits)
+// Shared-memory histogram update of one warp.  Keys of a segment share their high bits, so a whole warp
+// often hits ONE bin: that case costs a vote and a single atomic; otherwise plain atomics (few conflicts).
 __device__ __forceinline__ void hist_add(u32 *sh, u32 bin, bool valid)
 {
-	u32 peers = __match_any_sync(0xffffffffu, valid ? bin : 0xffffffffu);
-	if (valid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[bin], (u32)__popc(peers));
+	const u32 vmask = __ballot_sync(0xffffffffu, valid);
+	if (vmask == 0) return;
+	const int leader = __ffs(vmask) - 1;
+	const u32 b0 = __shfl_sync(0xffffffffu, bin, leader);
+	if (__all_sync(0xffffffffu, !valid || bin == b0))
+	{
+		if ((int)(threadIdx.x & 31) == leader) atomicAdd(&sh[b0], (u32)__popc(vmask));
+	}
+	else if (valid) atomicAdd(&sh[bin], 1u);
 }
 
 __device__ __forceinline__ void hist_flush(const u32 *sh, u32 *__restrict__ gh, int bins)
@@ -532,8 +540,7 @@ kd_bottom_kernel(TreeGeom g, const float *__restrict__ pos, const u32 *__restric
 						valid = c != ~0ull && (pass == 0 || (key >> (lo + 8)) == (s.sel[q].prefix >> (lo + 8)));
 						bin = (u32)q * 256u + ((key >> lo) & 255u);
 					}
-					u32 peers = __match_any_sync(0xffffffffu, valid ? bin : 0xffffffffu);
-					if (valid && lane == __ffs(peers) - 1) atomicAdd(&s.hist[bin], (u32)__popc(peers));
+					hist_add(s.hist, bin, valid);
 				}
 				__syncthreads();
 				if (warp < nblk)
@@ -798,7 +805,7 @@ void kd_release(KdTree &t)
 	for (DevBuf *b : all) b->release();
 }
 
-int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos)
+int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom)
 {
 	cudaStream_t st = ctx->stream;
 	const int64_t n = t.n;
@@ -842,6 +849,7 @@ int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos)
 		ctx->launches += 9;
 		iin = iout;
 	}
+	if (ev_bottom) NBCO_CUDA(cudaEventRecord(ev_bottom, st));
 	if (!t.bottom_attr)
 	{
 		NBCO_CUDA(cudaFuncSetAttribute(kd_bottom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBottomSmemBytes));

@@ -48,7 +48,7 @@ def next_eval_rebuilds(ctx):
         return True
 
 
-def fmm_leapfrog_sharded(ctx, buf, n, d_param, dt, nsteps, group=None):
+def fmm_leapfrog_sharded(ctx, buf, n, d_param, dt, nsteps, group=None, gather_final=True):
     """Leapfrog steps of coulombOscillatorFMMKD3 over `world` GPUs (one process per GPU).
 
     Partition: rank r of 2^g owns the subtree of kd node (g, r), i.e. the
@@ -98,5 +98,6 @@ def fmm_leapfrog_sharded(ctx, buf, n, d_param, dt, nsteps, group=None):
             gather(vel, b, e)                                                     # the rebuild permutes everything
         ctx.coulomb_fmm3_kd(p0, p0 + 4 * 6 * n, n, d_param)                       # a = f(x)     (own range written)
         ctx.step(p0 + 4 * (3 * n + 3 * b), p0 + 4 * (6 * n + 3 * b), half, cnt)   # v += a dt/2
-    gather(vel, b, e)
-    gather(acc, b, e)
+    if gather_final:   # leave the full state on every rank (callers that only read their own range skip this)
+        gather(vel, b, e)
+        gather(acc, b, e)
