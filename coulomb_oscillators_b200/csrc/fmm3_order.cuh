@@ -70,6 +70,56 @@ leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L)
 	}
 }
 
+// same result with G lanes per leaf, for leaves of more than 8 particles (orders >= 4): particles are
+// loaded one per lane, the centre is still the SEQUENTIAL fp32 sum (lane 0 adds the shuffled values in
+// storage order, bit-exact), the P2M sums are accumulated per lane and reduced by butterfly shuffles
+template <int P, int G>
+__global__ void __launch_bounds__(128)
+leaf_p2m_group_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L)
+{
+	const int m = 1 << L, beg = kd_beg(L);
+	const int lane = threadIdx.x & (G - 1);
+	const int groups = (gridDim.x * blockDim.x) / G;
+	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) / G; i < m; i += groups)
+	{
+		const int64_t st = seg_start(n, i, L);
+		const int cnt = (int)(seg_start(n, i + 1, L) - st);
+		const float *p = spos + 3 * st;
+		float cx = 0.f, cy = 0.f, cz = 0.f;
+		for (int j0 = 0; j0 < cnt; j0 += G)
+		{
+			const int j = j0 + lane;
+			const float x = j < cnt ? p[3*j] : 0.f, y = j < cnt ? p[3*j+1] : 0.f, z = j < cnt ? p[3*j+2] : 0.f;
+			const int nj = min(G, cnt - j0);
+			for (int k = 0; k < nj; ++k)
+			{
+				cx += __shfl_sync(gmask, x, k, G); cy += __shfl_sync(gmask, y, k, G); cz += __shfl_sync(gmask, z, k, G);
+			}
+		}
+		if (cnt > 0) { const float f = (float)cnt; cx = __fdiv_rn(cx, f); cy = __fdiv_rn(cy, f); cz = __fdiv_rn(cz, f); }
+		float M[pad4<sym_off(P)>()];
+#pragma unroll
+		for (int k = 0; k < pad4<sym_off(P)>(); ++k) M[k] = 0.f;
+		if constexpr (P >= 3)
+		{
+			for (int j = lane; j < cnt; j += G)
+				p2m_acc<P>(M, p[3*j] - cx, p[3*j+1] - cy, p[3*j+2] - cz);
+#pragma unroll
+			for (int k = sym_off(2); k < sym_off(P); ++k)
+#pragma unroll
+				for (int o = G / 2; o > 0; o >>= 1)
+					M[k] += __shfl_xor_sync(gmask, M[k], o, G);
+		}
+		if (lane == 0)
+		{
+			M[0] = (float)cnt;
+			t.center[beg + i] = make_float4(cx, cy, cz, t.size2[beg + i]);
+			store_tuple<sym_off(P)>(t.mpole + (int64_t)(beg + i) * t.sM, M);
+		}
+	}
+}
+
 // one parent from its two children (fmm_buildTree3_kdtree2_krnl, :328-368)
 template <int P>
 __device__ __forceinline__ void m2m_node(const TreeData &t, int node, int64_t n, int l, int i)
@@ -236,7 +286,11 @@ struct OrderImpl
 	static void upward(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L)
 	{
 		cudaStream_t st = ctx->stream;
-		leaf_p2m_kernel<P><<<grid_for(1ll << L, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L); ++ctx->launches;
+		const int mlt_max = (int)((n - 1) / (1ll << L) + 1);
+		if (mlt_max <= 8) leaf_p2m_kernel<P><<<grid_for(1ll << L, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L);
+		else if (mlt_max <= 16) leaf_p2m_group_kernel<P, 16><<<grid_for(16ll << L, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L);
+		else leaf_p2m_group_kernel<P, 32><<<grid_for(32ll << L, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L);
+		++ctx->launches;
 		for (int l = L - 1; l > kTopLevels; --l)
 		{
 			m2m_level_kernel<P><<<((1 << l) + 127) / 128, 128, 0, st>>>(t, n, l); ++ctx->launches;

@@ -372,7 +372,7 @@ struct GenImpl
 	const OrderOps kOrderOps##P = {GenImpl<P>::upward, GenImpl<P>::m2l, GenImpl<P>::downward};
 
 #ifndef NBCO_STATIC_ORDER_MAX
-#define NBCO_STATIC_ORDER_MAX 3
+#define NBCO_STATIC_ORDER_MAX 5
 #endif
 #if NBCO_STATIC_ORDER_MAX < 4
 NBCO_GENERIC_ORDER(4)

@@ -74,6 +74,10 @@ NBCO_HD void p2m_acc(float *M /* sym_off(P) */, float dx, float dy, float dz)
 }
 
 // ---- M2M: shift a child tuple (orders 0..P-1, dipole slot zero) by d = new - old centre, orders 2..P-1 ----
+// Source-driven form of (:1111-1146): the source term M_s[a,b,c] (order s) lands on the target entry
+// [a+k1, b+k2, c+k3] of order s+m with weight C(a+k1,k1) C(b+k2,k2) C(c+k3,k3) s!/(s+m)! d^k.  Same terms as the
+// target-driven sum, but every loop bound is a plain triangle (the max/min bounds of the target-driven nest made
+// nvcc's unroller explode: order 4 did not compile in 15 minutes).
 template <int P>
 NBCO_HD void m2m_acc(float *Mout, const float *Min, float dx, float dy, float dz)
 {
@@ -81,30 +85,29 @@ NBCO_HD void m2m_acc(float *Mout, const float *Min, float dx, float dy, float dz
 	{
 		Pow3<P - 1> pw(dx, dy, dz);
 		NBCO_UNROLL
-		for (int n = 2; n <= P - 1; ++n)
+		for (int s = 0; s <= P - 1; ++s)
+		{
+			if (s == 1) continue; // dipole of a centre-of-charge expansion is zero
 			NBCO_UNROLL
-			for (int z = 0; z <= n; ++z)
+			for (int c = 0; c <= s; ++c)
 				NBCO_UNROLL
-				for (int x = n - z; x >= 0; --x)
+				for (int a = 0; a <= s - c; ++a)
 				{
-					const int y = n - x - z;
-					float t = 0.f;
+					const int b = s - a - c;
+					const float src = Min[sym_off(s) + sym_idx(a, c, s)];
 					NBCO_UNROLL
-					for (int m = 0; m <= n; ++m)
-					{
-						if (n - m == 1) continue; // dipole of a centre-of-charge expansion is zero
+					for (int m = (s >= 2 ? 0 : 2); m <= P - 1 - s; ++m) // targets of order n = s + m in 2..P-1
 						NBCO_UNROLL
-						for (int k1 = 0; k1 <= (x < m ? x : m); ++k1)
+						for (int k3 = 0; k3 <= m; ++k3)
 							NBCO_UNROLL
-							for (int k3 = (m - k1 - y > 0 ? m - k1 - y : 0); k3 <= (z < m - k1 ? z : m - k1); ++k3)
+							for (int k1 = 0; k1 <= m - k3; ++k1)
 							{
-								const int k2 = m - k1 - k3;
-								const float c = (float)(cbinom(x, k1) * cbinom(y, k2) * cbinom(z, k3) * cfact(n - m) / cfact(n));
-								t += c * pw.x[k1] * pw.y[k2] * pw.z[k3] * Min[sym_off(n - m) + sym_idx(x - k1, z - k3, n - m)];
+								const int k2 = m - k1 - k3, n = s + m;
+								const float w = (float)(cbinom(a + k1, k1) * cbinom(b + k2, k2) * cbinom(c + k3, k3) * cfact(s) / cfact(n));
+								Mout[sym_off(n) + sym_idx(a + k1, c + k3, n)] += w * pw.x[k1] * pw.y[k2] * pw.z[k3] * src;
 							}
-					}
-					Mout[sym_off(n) + sym_idx(x, z, n)] += t;
 				}
+		}
 	}
 }
 
