@@ -7,6 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 lib_path = os.path.join(_HERE, "libnbco.so")
 
 EVAL_DIRECT3, EVAL_FMM3_KD, EVAL_COULOMB_DIRECT3, EVAL_COULOMB_FMM3_KD = 0, 1, 2, 3
+EVAL_DIRECT2, EVAL_FMM2, EVAL_COULOMB_DIRECT2, EVAL_COULOMB_FMM2 = 4, 5, 6, 7
 EULER, LEAPFROG, FORESTRUTH, PEFRL = 0, 1, 2, 3
 
 
@@ -19,7 +20,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("order", C.c_int32), ("radius", C.c_float), ("eps2", C.c_float),
                 ("dens_inhom", C.c_float), ("max_level", C.c_int32), ("tree_steps", C.c_int32),
                 ("coll", C.c_int32), ("unsort", C.c_int32), ("m2l_first", C.c_int32),
-                ("rank", C.c_int32), ("world", C.c_int32)]
+                ("rank", C.c_int32), ("world", C.c_int32), ("eps2_d", C.c_double)]
 
 
 class FmmInfo(C.Structure):
@@ -29,6 +30,11 @@ class FmmInfo(C.Structure):
                 ("counter", C.c_int32), ("reserved", C.c_int32)]
 
 
+class Fmm2Info(C.Structure):
+    _fields_ = [("levels", C.c_int32), ("order", C.c_int32), ("n", C.c_int64), ("nodes", C.c_int64),
+                ("coeffs", C.c_int32), ("reserved", C.c_int32), ("kernel_launches", C.c_int64), ("evals", C.c_int64)]
+
+
 # every symbol include/nbco.h declares (tests/test_abi.py checks this list against the header)
 SYMBOLS = [
     "nbco_default_config", "nbco_abi_version", "nbco_last_error", "nbco_create", "nbco_destroy",
@@ -36,6 +42,10 @@ SYMBOLS = [
     "nbco_coulomb_direct3", "nbco_coulomb_fmm3_kd", "nbco_add_elastic", "nbco_step", "nbco_compute_force",
     "nbco_integrate", "nbco_mean_rel_err", "nbco_energy", "nbco_eval_host", "nbco_run_host", "nbco_step_host",
     "nbco_fmm_get_info", "nbco_fmm_get_tree", "nbco_fmm_get_lists", "nbco_fmm_get_phase_ms", "nbco_fmm_phase_totals",
+    "nbco_force_direct2", "nbco_force_fmm2", "nbco_coulomb_direct2", "nbco_coulomb_fmm2", "nbco_add_elastic2", "nbco_step2",
+    "nbco_compute_force2", "nbco_integrate2", "nbco_mean_rel_err2", "nbco_energy2", "nbco_run_host2", "nbco_step_host2",
+    "nbco_fmm2_levels", "nbco_fmm2_get_info", "nbco_fmm2_get_tree", "nbco_fmm2_get_phase_ms",
+    "nbco_init_ga2", "nbco_init_kv2", "nbco_beam_params2", "nbco_state_read2", "nbco_state_write2",
     "nbco_shard_range", "nbco_init_ga", "nbco_init_test_cube", "nbco_state_read", "nbco_state_write", "nbco_free",
 ]
 
@@ -79,6 +89,25 @@ def _load():
     L.nbco_state_read.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(i64)]
     L.nbco_state_write.argtypes = [C.c_char_p, vp, i64]
     L.nbco_free.argtypes = [vp]
+    # 2D fp64 path
+    for f in ("nbco_force_direct2", "nbco_force_fmm2", "nbco_coulomb_direct2", "nbco_coulomb_fmm2", "nbco_add_elastic2"):
+        getattr(L, f).argtypes = [vp, vp, vp, i64, vp]
+    L.nbco_step2.argtypes = [vp, vp, vp, f64, i64]
+    L.nbco_compute_force2.argtypes = [vp, C.c_int, vp, i64, vp]
+    L.nbco_integrate2.argtypes = [vp, C.c_int, C.c_int, vp, i64, vp, f64, i64]
+    L.nbco_mean_rel_err2.argtypes = [vp, vp, vp, i64, C.POINTER(f64), C.POINTER(f64)]
+    L.nbco_energy2.argtypes = [vp, vp, i64, vp, C.POINTER(f64)]
+    L.nbco_run_host2.argtypes = [vp, C.c_int, C.c_int, vp, vp, i64, vp, f64, i64]
+    L.nbco_step_host2.argtypes = [vp, C.c_int, C.c_int, vp, i64, vp, f64, i64]
+    L.nbco_fmm2_levels.argtypes = [i64, C.c_int32, f64]
+    L.nbco_fmm2_get_info.argtypes = [vp, C.POINTER(Fmm2Info)]
+    L.nbco_fmm2_get_tree.argtypes = [vp] + [vp] * 6
+    L.nbco_fmm2_get_phase_ms.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(f32), C.c_int]
+    L.nbco_init_ga2.argtypes = [vp, i64, vp, vp]
+    L.nbco_init_kv2.argtypes = [vp, i64, vp, vp]
+    L.nbco_beam_params2.argtypes = [vp, vp, f64, vp]
+    L.nbco_state_read2.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(i64)]
+    L.nbco_state_write2.argtypes = [C.c_char_p, vp, i64]
     L.nbco_free.restype = None
     return L
 
@@ -130,6 +159,49 @@ def init_test_cube(n, sigma_x=(0.003, 0.001, 0.01), omega0=(1.095, 1.0, 1.0)):
     out = np.empty((2, n, 3), np.float32)
     _check(lib.nbco_init_test_cube(_hp(out), n, _hp(sx), _hp(su)))
     return out
+
+
+TWOPI = 6.283185307179586476925286766559
+OMEGA0_2D = (6.22 * TWOPI, 6.21 * TWOPI)   # main.cu:272
+EMIT_2D = (0.03e-3, 0.01e-3)               # main.cu:294
+
+
+def beam_params2(omega0=OMEGA0_2D, emit=EMIT_2D, tune_dep_y=0.8):
+    """default beam of main.cu:294-313: dict A (2), omega (2), xi"""
+    o = np.zeros(5)
+    _check(lib.nbco_beam_params2(_hp(np.asarray(omega0, np.float64)), _hp(np.asarray(emit, np.float64)), tune_dep_y, _hp(o)))
+    return dict(A=o[0:2].copy(), omega=o[2:4].copy(), xi=float(o[4]))
+
+
+def default_param2(n, xi=None, omega0=OMEGA0_2D):
+    """parameter block of main.cu:803-808: {xi/N, 0, w0x^2, w0y^2} (float64)"""
+    if xi is None:
+        xi = beam_params2(omega0)["xi"]
+    return np.array([xi / n, 0.0, omega0[0] * omega0[0], omega0[1] * omega0[1]], np.float64)
+
+
+def init_kv2(n, A=None, omega=None):
+    """reference initKV state [pos|vel] as a (2, n, 2) float64 array (main.cu:120-145,779-784)"""
+    b = beam_params2()
+    A = np.asarray(b["A"] if A is None else A, np.float64)
+    omega = np.asarray(b["omega"] if omega is None else omega, np.float64)
+    out = np.empty((2, n, 2), np.float64)
+    _check(lib.nbco_init_kv2(_hp(out), n, _hp(A), _hp(omega)))
+    return out
+
+
+def init_ga2(n, x=None, u=None):
+    """reference 2D initGA state (main.cu:147-170): std.dev. x = A/2, u = omega*A/2 by default (:312-313)"""
+    b = beam_params2()
+    x = np.asarray(b["A"] / 2 if x is None else x, np.float64)
+    u = np.asarray(b["omega"] * b["A"] / 2 if u is None else u, np.float64)
+    out = np.empty((2, n, 2), np.float64)
+    _check(lib.nbco_init_ga2(_hp(out), n, _hp(x), _hp(u)))
+    return out
+
+
+def fmm2_levels(n, order, dens_inhom=1.0):
+    return lib.nbco_fmm2_levels(n, order, dens_inhom)
 
 
 def shard_range(n, rank, world):
@@ -250,6 +322,75 @@ class Context:
         ev = (C.c_int64 * 2)()
         k = lib.nbco_fmm_phase_totals(self._h, names, ms, 32, ev, 1 if reset else 0)
         return {names[j].decode(): ms[j] for j in range(k)}, ev[0], ev[1]
+
+    # ---- 2D fp64 path ----
+    def force_direct2(self, d_pos, d_acc, n, d_param=None):
+        _check(lib.nbco_force_direct2(self._h, d_pos, d_acc, n, d_param))
+
+    def force_fmm2(self, d_pos, d_acc, n, d_param=None):
+        _check(lib.nbco_force_fmm2(self._h, d_pos, d_acc, n, d_param))
+
+    def coulomb_direct2(self, d_pos, d_acc, n, d_param=None):
+        _check(lib.nbco_coulomb_direct2(self._h, d_pos, d_acc, n, d_param))
+
+    def coulomb_fmm2(self, d_pos, d_acc, n, d_param=None):
+        _check(lib.nbco_coulomb_fmm2(self._h, d_pos, d_acc, n, d_param))
+
+    def add_elastic2(self, d_pos, d_acc, n, d_k2=None):
+        _check(lib.nbco_add_elastic2(self._h, d_pos, d_acc, n, d_k2))
+
+    def step2(self, d_b, d_a, ds, n):
+        _check(lib.nbco_step2(self._h, d_b, d_a, ds, n))
+
+    def compute_force2(self, evaluator, d_buf, n, d_param=None):
+        _check(lib.nbco_compute_force2(self._h, evaluator, d_buf, n, d_param))
+
+    def integrate2(self, scheme, evaluator, d_buf, n, d_param, dt, nsteps):
+        _check(lib.nbco_integrate2(self._h, scheme, evaluator, d_buf, n, d_param, dt, nsteps))
+
+    def mean_rel_err2(self, d_a, d_ref, n):
+        m, x = C.c_double(), C.c_double()
+        _check(lib.nbco_mean_rel_err2(self._h, d_a, d_ref, n, C.byref(m), C.byref(x)))
+        return m.value, x.value
+
+    def energy2(self, d_buf, n, d_param=None):
+        out = (C.c_double * 3)()
+        _check(lib.nbco_energy2(self._h, d_buf, n, d_param, out))
+        return tuple(out)
+
+    def run_host2(self, scheme, evaluator, pos_vel, param, dt, nsteps, want_acc=False):
+        """pos_vel (2,n,2) float64, updated in place"""
+        n = pos_vel.shape[1]
+        acc = np.empty((n, 2), np.float64) if want_acc else None
+        _check(lib.nbco_run_host2(self._h, scheme, evaluator, _hp(pos_vel), _hp(acc), n, _hp(param), dt, nsteps))
+        return acc
+
+    def step_host2(self, scheme, evaluator, buf, n, param, dt, nsteps=1):
+        """buf: flat float64 [pos|vel|acc] (6n), updated in place"""
+        _check(lib.nbco_step_host2(self._h, scheme, evaluator, _hp(buf), n, _hp(param), dt, nsteps))
+
+    def fmm2_info(self):
+        info = Fmm2Info()
+        _check(lib.nbco_fmm2_get_info(self._h, C.byref(info)))
+        return info
+
+    def fmm2_tree(self):
+        """center (nodes,) complex, mpole/local (nodes, order+1) complex, mult, leaf_index (4^L+1), perm"""
+        i = self.fmm2_info()
+        nn, c, m = i.nodes, i.coeffs, 1 << (2 * i.levels)
+        t = dict(center=np.empty(nn, np.complex128), mpole=np.empty((nn, c), np.complex128),
+                 local=np.empty((nn, c), np.complex128), mult=np.empty(nn, np.int32),
+                 leaf_index=np.empty(m + 1, np.int32), perm=np.empty(i.n, np.int32))
+        _check(lib.nbco_fmm2_get_tree(self._h, _hp(t["center"]), _hp(t["mpole"]), _hp(t["local"]), _hp(t["mult"]),
+                                      _hp(t["leaf_index"]), _hp(t["perm"])))
+        t["levels"] = i.levels
+        return t
+
+    def fmm2_phase_ms(self):
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        k = lib.nbco_fmm2_get_phase_ms(self._h, names, ms, 16)
+        return {names[j].decode(): ms[j] for j in range(k)}
 
     def fmm_phase_ms(self):
         names = (C.c_char_p * 32)()

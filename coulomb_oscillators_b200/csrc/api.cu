@@ -48,7 +48,7 @@ void DevBuf::release()
 
 static int check_cfg(const nbco_config *c)
 {
-	if (c->order < 1 || c->order > NBCO_MAX_ORDER) { set_error("order %d outside 1..%d", c->order, NBCO_MAX_ORDER); return NBCO_ERR_INVALID; }
+	if (c->order < 1 || c->order > NBCO2_MAX_ORDER) { set_error("order %d outside 1..%d", c->order, NBCO2_MAX_ORDER); return NBCO_ERR_INVALID; }
 	if (!(c->radius > 0.f)) { set_error("radius must be > 0"); return NBCO_ERR_INVALID; }
 	if (!(c->eps2 > 0.f)) { set_error("eps2 must be > 0 (the i = j term is 0 * rsqrt(eps2))"); return NBCO_ERR_INVALID; }
 	if (!(c->dens_inhom > 0.f)) { set_error("dens_inhom must be > 0"); return NBCO_ERR_INVALID; }
@@ -166,6 +166,7 @@ void nbco_default_config(nbco_config *cfg)
 	cfg->m2l_first = 1;      // what the reference GPU path launches (fmm_cart3_kdtree.cuh:1668)
 	cfg->rank = 0;
 	cfg->world = 1;
+	cfg->eps2_d = 1.e-18;    // EPS2 with SCAL = double (2D path)
 }
 
 int nbco_abi_version(void) { return NBCO_ABI_VERSION; }
@@ -201,6 +202,7 @@ void nbco_destroy(nbco_ctx *ctx)
 	cudaSetDevice(ctx->cfg.device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	fmm3_destroy(ctx);
+	fmm2_destroy(ctx);
 	ctx->pos4.release(); ctx->red.release(); ctx->h_state.release(); ctx->h_param.release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -42,6 +42,7 @@ struct DevBuf
 };
 
 struct FmmPlan; // fmm3.cu
+struct Fmm2Plan; // fmm2.cu
 
 } // namespace nbco
 
@@ -62,6 +63,7 @@ struct nbco_ctx
 	void *pinned = nullptr; size_t pinned_bytes = 0;
 
 	nbco::FmmPlan *fmm = nullptr;
+	nbco::Fmm2Plan *fmm2 = nullptr;
 };
 
 namespace nbco {
@@ -78,6 +80,13 @@ int kinetic_elastic_launch(nbco_ctx *ctx, const float *d_buf, int64_t n, const f
 // fmm3.cu
 int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const float *d_param, bool fuse_elastic);
 void fmm3_destroy(nbco_ctx *ctx);
+// fmm2.cu (2D fp64 path)
+int fmm2_launch(nbco_ctx *ctx, double *d_pos, double *d_acc, int64_t n, const double *d_param, bool fuse_elastic);
+int direct2_launch(nbco_ctx *ctx, const double *d_pos, double *d_acc, int64_t n, const double *d_param);
+int step2_launch(nbco_ctx *ctx, double *d_b, const double *d_a, double ds, int64_t n);
+int kick_drift2_launch(nbco_ctx *ctx, double *d_pos, double *d_vel, const double *d_acc, double kc, double dc, int64_t n);
+int add_elastic2_launch(nbco_ctx *ctx, const double *d_pos, double *d_acc, int64_t n, const double *d_k2);
+void fmm2_destroy(nbco_ctx *ctx);
 
 inline int grid_for(int64_t work, int block, int sm_count, int per_sm)
 {

@@ -487,6 +487,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 
 int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const float *d_param, bool fuse_elastic)
 {
+	if (ctx->cfg.order > NBCO_MAX_ORDER) { set_error("fmm3_kd: order %d outside 1..%d", ctx->cfg.order, NBCO_MAX_ORDER); return NBCO_ERR_INVALID; }
 	if (ctx->cfg.world != 1)
 	{
 		// sharded evaluation: the tree is replicated, every rank computes the accelerations of its own subtree

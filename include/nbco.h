@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NBCO_ABI_VERSION 1
+#define NBCO_ABI_VERSION 2
 
 typedef struct nbco_ctx nbco_ctx;
 
@@ -62,9 +62,12 @@ typedef struct nbco_config
 	                          0 = leaf test first (reference CPU path, :586-598) */
 	int32_t rank;          /* multi-GPU: this process' rank and the world size; the evaluators then */
 	int32_t world;         /* compute only this rank's shard of targets (see nbco_shard_range)      */
+	double  eps2_d;        /* EPS2 of the 2D fp64 path (SCAL = double, constants.cuh:39); default 1e-18;
+	                          0 = use (double)eps2 */
 } nbco_config;
 
-#define NBCO_MAX_ORDER 6
+#define NBCO_MAX_ORDER 6    /* 3D kd-tree FMM */
+#define NBCO2_MAX_ORDER 10  /* 2D FMM (the reference's -test loop runs p = 1..10, main.cu:844) */
 
 void nbco_default_config(nbco_config *cfg);
 int  nbco_abi_version(void);
@@ -171,6 +174,69 @@ int nbco_fmm_get_phase_ms(nbco_ctx *ctx, const char **names, float *ms, int cap)
  * number of evaluations and how many of them rebuilt the tree in h_evals[0], h_evals[1].
  * reset != 0 clears the sums after reading.  Returns the number of phases. */
 int nbco_fmm_phase_totals(nbco_ctx *ctx, const char **names, double *ms, int cap, int64_t *h_evals, int reset);
+
+/* ==== 2D fp64 path (the reference's `nbco` binary: SCAL = double, VEC = double2, DIM = 2) ====
+ * State buffer [pos(n) | vel(n) | acc(n)] of double2; param is a DEVICE array {xi/N, 0, kx, ky}
+ * (main.cu:803-808): the Coulomb evaluators read param[0], the elastic term reads param+2.
+ * nbco_force_fmm2 replaces fmm_cart (fmm_cart.cuh:395-545): like the reference it ALWAYS permutes pos
+ * and the velocities stored at pos+n into cell order (:500-505; there is no unsort in 2D) and rebuilds
+ * the grid on every call.  cfg.order 1..NBCO2_MAX_ORDER, cfg.radius is truncated to int (:398),
+ * cfg.eps2_d, cfg.dens_inhom, cfg.coll and cfg.max_level (0 = automatic, :416-418) apply. */
+int nbco_force_direct2(nbco_ctx *ctx, const void *d_pos, void *d_acc, int64_t n, const void *d_param);  /* direct2, direct.cuh:166-179 */
+int nbco_force_fmm2(nbco_ctx *ctx, void *d_pos, void *d_acc, int64_t n, const void *d_param);
+/* coulombOscillatorDirect / coulombOscillatorFMM (main.cu:69-89) */
+int nbco_coulomb_direct2(nbco_ctx *ctx, void *d_pos, void *d_acc, int64_t n, const void *d_param);
+int nbco_coulomb_fmm2(nbco_ctx *ctx, void *d_pos, void *d_acc, int64_t n, const void *d_param);
+int nbco_add_elastic2(nbco_ctx *ctx, const void *d_pos, void *d_acc, int64_t n, const void *d_k2);
+int nbco_step2(nbco_ctx *ctx, void *d_b, const void *d_a, double ds, int64_t n);
+
+enum nbco_evaluator2 { NBCO_EVAL_DIRECT2 = 4, NBCO_EVAL_FMM2 = 5, NBCO_EVAL_COULOMB_DIRECT2 = 6, NBCO_EVAL_COULOMB_FMM2 = 7 };
+int nbco_compute_force2(nbco_ctx *ctx, int evaluator, void *d_buf, int64_t n, const void *d_param);
+/* integrator.cuh:32-167 with SCAL = double; schemes as nbco_scheme */
+int nbco_integrate2(nbco_ctx *ctx, int scheme, int evaluator, void *d_buf, int64_t n,
+                    const void *d_param, double dt, int64_t nsteps);
+int nbco_mean_rel_err2(nbco_ctx *ctx, const void *d_a, const void *d_ref, int64_t n, double *h_mean, double *h_max);
+/* h_out[0] = sum 1/2 v^2, h_out[1] = 1/2 sum k o x^2, h_out[2] = param[0] * sum_{i<j} -1/2 log(d^2+eps2)
+ * (the potential whose gradient is the 2D kernel d/(d^2+eps2), direct.cuh:23-31); O(n^2). */
+int nbco_energy2(nbco_ctx *ctx, const void *d_buf, int64_t n, const void *d_param, double *h_out3);
+/* host state [pos|vel] (4n doubles, the state-file layout): H2D, compute_force, nsteps steps, D2H */
+int nbco_run_host2(nbco_ctx *ctx, int scheme, int evaluator, double *h_pos_vel, double *h_acc, int64_t n,
+                   const double *h_param, double dt, int64_t nsteps);
+/* nsteps steps from a host buffer [pos|vel|acc] (6n doubles, acc valid on entry): H2D, steps, D2H */
+int nbco_step_host2(nbco_ctx *ctx, int scheme, int evaluator, double *h_buf, int64_t n,
+                    const double *h_param, double dt, int64_t nsteps);
+
+typedef struct nbco_fmm2_info
+{
+	int32_t levels;        /* L: the leaf grid is 2^L x 2^L, levels 2..L carry expansions */
+	int32_t order;
+	int64_t n;
+	int64_t nodes;         /* (4^(L+1)-1)/3, node (i,j) of level l at (4^l-1)/3 + i*2^l + j (fmm_cart.cuh tree_beg) */
+	int32_t coeffs;        /* complex coefficients per node and expansion: order + 1 */
+	int32_t reserved;
+	int64_t kernel_launches;
+	int64_t evals;
+} nbco_fmm2_info;
+int nbco_fmm2_levels(int64_t n, int32_t order, double dens_inhom);   /* fmm_cart.cuh:416-418 */
+int nbco_fmm2_get_info(nbco_ctx *ctx, nbco_fmm2_info *info);
+/* Copies to host whatever is non-NULL.  center: double2 per node.  mpole / local: `coeffs` complex numbers
+ * (re, im) per node -- the harmonic content of the reference's tuples: mpole[q] = sum_k binom(q,k) i^k M_q[k]
+ * of the symmetric tuple M_q (fmm_cart_base.cuh:111), local[n] = L_n[0] + i L_n[1] of the traceless tuple
+ * (:116).  mult: int per node.  leaf_index: 4^L + 1 ints, first particle of every leaf cell (indexLeaves).
+ * perm[n]: sorted position -> position in the array passed to the last call. */
+int nbco_fmm2_get_tree(nbco_ctx *ctx, double *h_center, double *h_mpole, double *h_local, int32_t *h_mult,
+                       int32_t *h_leaf_index, int32_t *h_perm);
+int nbco_fmm2_get_phase_ms(nbco_ctx *ctx, const char **names, float *ms, int cap);
+
+/* 2D initial conditions and state files (host side, byte-compatible with main.cu) */
+/* initGA (main.cu:147-170) / initKV (:120-145) with the fixed seed and discard of main.cu:779-784;
+ * h_pos_vel = 4n doubles.  GA: std.dev. x2, u2.  KV: semi-axes A2, depressed phase advances omega2. */
+int nbco_init_ga2(double *h_pos_vel, int64_t n, const double *x2, const double *u2);
+int nbco_init_kv2(double *h_pos_vel, int64_t n, const double *A2, const double *omega2);
+/* default beam of main.cu:272,294-313 from omega0 and the emittances: out = {A.x, A.y, omega.x, omega.y, xi} */
+int nbco_beam_params2(const double *omega0_2, const double *emit2, double tune_dep_y, double *out5);
+int nbco_state_read2(const char *path, double **h_pos_vel, int64_t *n);  /* caller frees with nbco_free */
+int nbco_state_write2(const char *path, const double *h_pos_vel, int64_t n);
 
 /* ---- multi-GPU helpers ---- */
 /* Target shard [begin, end) of rank r of w over n items: the kd-tree's own equal split

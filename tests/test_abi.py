@@ -26,11 +26,12 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_defaults():
     import coulomb_oscillators_b200 as nb
-    assert nb.lib.nbco_abi_version() == 1
+    assert nb.lib.nbco_abi_version() == 2
     cfg = nb._lib.default_config()
     # defaults of reference constants.cuh:36-52
     assert (cfg.order, cfg.tree_steps, cfg.coll, cfg.unsort, cfg.max_level) == (3, 8, 1, 1, 0)
     assert cfg.radius == 1.0 and abs(cfg.eps2 - 1e-18) < 1e-24 and cfg.dens_inhom == 1.0
+    assert cfg.eps2_d == 1e-18
 
 
 def test_no_cpu_fallback():
@@ -46,4 +47,4 @@ def test_no_cpu_fallback():
 def test_product_does_not_link_oracle():
     import coulomb_oscillators_b200._lib as L
     blob = open(L.lib_path, "rb").read()
-    assert b"orc_fmm3_kd" not in blob and b"libnbco_oracle" not in blob and b"libnbco_ref" not in blob
+    assert b"orc_fmm3_kd" not in blob and b"orc2_fmm" not in blob and b"libnbco_oracle" not in blob and b"libnbco_ref" not in blob
