@@ -16,7 +16,8 @@
 //     = sum_j (-(z_j - c))^q / q!, and a traceless order-n local is L_n = L_n[0] + i L_n[1]; so
 //        P2M  Z_q  = sum_j (-(z_j - c))^q / q!
 //        M2M  Z'_n = sum_m Z_(n-m) d^m / m!,                  d = c_parent - c_child
-//        M2L  L_n += 1/n! sum_q conj(Z_q) g_(n+q),            g_m = (-1)^m (m-1)! w^m, w = dz / (|dz|^2 + eps2)
+//        M2L  L_n += 1/n! sum_q conj(Z_q) g_(n+q),            g_m = (-1)^m (m-1)! r^-m (T_m(d0) + i d1 U_(m-1)(d0)),
+//                                                             r^2 = |dz|^2 + eps2, d = dz / r (the reference's softened form)
 //        L2L  L'_q = sum_(m>=q) binom(m,q) L_m conj(d)^(m-q), d = c_child - c_parent
 //        L2P  f    = -sum_n n L_n conj(d)^(n-1)
 //     (tests/cx2d.py states these in numpy and tests/test_ops2d_host.py pins them to the oracle's
@@ -25,7 +26,7 @@
 //   * stable LSD radix sort of the 2L-bit cell keys written here (warp match ranking), one gather;
 //   * M2L and L2L of a level fused into one kernel (thread per target node, no atomics);
 //   * near field: thread per sorted particle, sources of the 2r+1 row runs read through L1
-//     (lanes of one cell broadcast), fp64 reciprocal = MUFU.RCP64H + 2 Newton steps, with L2P, the
+//     (lanes of one cell broadcast), fp64 reciprocal = MUFU.RCP64H + 6 DFMA, with L2P, the
 //     xi/N rescale and the elastic term fused into the same kernel (one write of acc).
 // There is no CPU path.
 
@@ -63,15 +64,16 @@ __device__ __forceinline__ void cfma_conj(double2 &s, double2 a, double2 b) // s
 	s.y = fma(a.x, b.y, s.y); s.y = fma(-a.y, b.x, s.y);
 }
 
-// 1/x for normal positive x: MUFU.RCP64H seed (>= 20 bits) + two Newton steps (error -> ~1 ulp)
+// 1/x for normal positive x: MUFU.RCP64H seed (measured: only ~2^-10 accurate) refined by two
+// third-order steps y <- y (1 + e + e^2), e = 1 - x y: relative error e^9, i.e. below 1 ulp
 __device__ __forceinline__ double rcp_nr(double x)
 {
 	double y;
 	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 	double e = fma(-x, y, 1.0);
-	y = fma(y, e, y);
+	y = fma(y, fma(e, e, e), y);
 	e = fma(-x, y, 1.0);
-	y = fma(y, e, y);
+	y = fma(y, fma(e, e, e), y);
 	return y;
 }
 
@@ -400,19 +402,26 @@ __global__ void __launch_bounds__(128) m2l_l2l2_kernel(Tree2 t, int l, int radiu
 				if (t.mult[s] <= 0) continue; // an empty source has Z = 0
 				const double2 cs = t.center[s];
 				const double dx = ct.x - cs.x, dy = ct.y - cs.y;
+				// The reference normalises by r = sqrt(|dz|^2 + eps2) (fmm_cart.cuh:241-249), so its direction
+				// d = dz / r is not a unit vector and its gradient tuple is the Chebyshev pair
+				// g_m = (-1)^m (m-1)! r^-m (T_m(d0), d1 U_(m-1)(d0)); both obey E_(m+1) = 2 d0 E_m - E_(m-1).
 				const double r2 = dx * dx + dy * dy + eps2;
-				const double inv = 1.0 / r2;
-				const double2 w = make_double2(dx * inv, dy * inv);
-				// G[m] = (-1)^m (m-1)! w^m, m = 1 .. 2P
+				const double r = sqrt(r2), ri = 1.0 / r;
+				const double d0 = dx / r, d1 = dy / r, two_d0 = 2.0 * d0;
 				double2 G[2 * P + 1];
 				G[0] = make_double2(0.0, 0.0);
-				G[1] = make_double2(-w.x, -w.y);
-#pragma unroll
-				for (int mm = 2; mm <= 2 * P; ++mm)
 				{
-					const double2 v = cmul(G[mm - 1], w);
-					const double f = -(double)(mm - 1);
-					G[mm] = make_double2(v.x * f, v.y * f);
+					double2 Em = make_double2(1.0, 0.0), E = make_double2(d0, d1);
+					double sc = -ri; // (-1)^m (m-1)! r^-m
+					G[1] = make_double2(sc * E.x, sc * E.y);
+#pragma unroll
+					for (int mm = 2; mm <= 2 * P; ++mm)
+					{
+						const double2 En = make_double2(fma(two_d0, E.x, -Em.x), fma(two_d0, E.y, -Em.y));
+						Em = E; E = En;
+						sc *= -(double)(mm - 1) * ri;
+						G[mm] = make_double2(sc * E.x, sc * E.y);
+					}
 				}
 				const double2 *zs = t.Z + (size_t)s * (P + 1);
 #pragma unroll

@@ -9,7 +9,7 @@ contraction with the traceless gradient only through  Z_q = sum_k binom(q,k) i^k
 L_n = L_n[0] + i L_n[1].  Then
   P2M   Z_q  = sum_j (-(z_j - c))^q / q!
   M2M   Z'_n = sum_m Z_{n-m} (c_child - c_parent)... see m2m()
-  M2L   L_n += 1/n! sum_q conj(Z_q) g_{n+q},  g_m = (-1)^m (m-1)! w^m,  w = (dx + i dy)/(dx^2+dy^2+eps2)
+  M2L   L_n += 1/n! sum_q conj(Z_q) g_{n+q},  g_m = (-1)^m (m-1)! E_m / r^m,  r^2 = dx^2+dy^2+eps2, see m2l()
   L2L   L'_q = sum_{m>=q} binom(m,q) L_m conj(d)^(m-q)
   L2P   f    = -sum_n n L_n conj(d)^(n-1)
 """
@@ -63,15 +63,21 @@ def m2m(Zc, d, p):
 
 
 def m2l(Zs, dz, p, eps2):
-    """dz = c_target - c_source"""
-    w = dz / (dz.real ** 2 + dz.imag ** 2 + eps2)
+    """dz = c_target - c_source.  The reference normalises by r = sqrt(|dz|^2 + eps2) (fmm_cart.cuh:241-249), so
+    its direction d = dz / r is NOT a unit vector and its gradient tuple is the Chebyshev pair
+    g_m = (-1)^m (m-1)! r^-m (T_m(d0), d1 U_(m-1)(d0)); both entries obey E_(m+1) = 2 d0 E_m - E_(m-1)."""
+    r = np.sqrt(dz.real ** 2 + dz.imag ** 2 + eps2)
+    d0, d1 = dz.real / r, dz.imag / r
+    E = [1.0 + 0j, d0 + 1j * d1]
+    for m in range(2, 2 * p + 1):
+        E.append(2 * d0 * E[m - 1] - E[m - 2])
     out = np.zeros(p + 1, complex)
     for n in range(p + 1):
         for q in range(p + 1):
             m = n + q
             if m == 0:
                 continue
-            g = (-1) ** m * factorial(m - 1) * w ** m
+            g = (-1) ** m * factorial(m - 1) * E[m] / r ** m
             out[n] += np.conj(Zs[q]) * g / factorial(n)
     out[0] = out[0].real
     return out

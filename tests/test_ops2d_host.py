@@ -59,7 +59,7 @@ def test_complex_operators_match_oracle(n, p):
                 mine[t] += cx2d.l2l(mine[par], c[t] - c[par], p)
         sel = slice(tb(l), tb(l + 1))
         err = (np.abs(mine[sel] - Lc[sel]) / np.abs(Lc[sel]).max(0)).max()
-        assert err <= 1e-10, (l, err)  # the Cartesian form evaluates order-2p polynomials in monomial form: ~1e-11
+        assert err <= 1e-12, (l, err)
     # L2P + near field = acc
     side = 1 << L
     far = np.zeros(n, complex)
