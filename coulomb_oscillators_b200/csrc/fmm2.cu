@@ -43,6 +43,7 @@ typedef unsigned int u32;
 constexpr int kB = 256;
 constexpr int kRsItems = 16;
 constexpr int kRsTile = kB * kRsItems; // keys per radix tile
+constexpr int kRsBits = 9, kRsBins = 1 << kRsBits; // digit width of one pass
 constexpr int kMaxP2 = NBCO2_MAX_ORDER;
 
 struct Grid2 { double minx, miny, rdelta, pad; };
@@ -75,6 +76,32 @@ __device__ __forceinline__ double rcp_nr(double x)
 	e = fma(-x, y, 1.0);
 	y = fma(y, fma(e, e, e), y);
 	return y;
+}
+
+// Four softened pair terms with ONE reciprocal (Montgomery's trick): 1/r_k = (prod of the others) / (r0 r1 r2 r3).
+// 9 DMUL + 6 DFMA + 1 MUFU for four inverses instead of 4 x (6 DFMA + MUFU); products stay far inside the
+// double range (r_k >= eps2).  Accumulation order is the source order, like the reference's loop.
+__device__ __forceinline__ void pair4(double px, double py, double2 q0, double2 q1, double2 q2, double2 q3, double eps2,
+                                      double &ax, double &ay)
+{
+	const double dx0 = px - q0.x, dy0 = py - q0.y, dx1 = px - q1.x, dy1 = py - q1.y;
+	const double dx2 = px - q2.x, dy2 = py - q2.y, dx3 = px - q3.x, dy3 = py - q3.y;
+	const double r0 = fma(dy0, dy0, fma(dx0, dx0, eps2)), r1 = fma(dy1, dy1, fma(dx1, dx1, eps2));
+	const double r2 = fma(dy2, dy2, fma(dx2, dx2, eps2)), r3 = fma(dy3, dy3, fma(dx3, dx3, eps2));
+	const double p01 = r0 * r1, p23 = r2 * r3;
+	const double I = rcp_nr(p01 * p23);
+	const double i01 = I * p23, i23 = I * p01;
+	const double v0 = i01 * r1, v1 = i01 * r0, v2 = i23 * r3, v3 = i23 * r2;
+	ax = fma(v0, dx0, ax); ay = fma(v0, dy0, ay);
+	ax = fma(v1, dx1, ax); ay = fma(v1, dy1, ay);
+	ax = fma(v2, dx2, ax); ay = fma(v2, dy2, ay);
+	ax = fma(v3, dx3, ax); ay = fma(v3, dy3, ay);
+}
+__device__ __forceinline__ void pair1(double px, double py, double2 q, double eps2, double &ax, double &ay)
+{
+	const double dx = px - q.x, dy = py - q.y;
+	const double inv = rcp_nr(fma(dy, dy, fma(dx, dx, eps2)));
+	ax = fma(inv, dx, ax); ay = fma(inv, dy, ay);
 }
 
 __host__ __device__ constexpr double binom_c(int n, int k)
@@ -119,10 +146,25 @@ __global__ void __launch_bounds__(kB) bbox2_kernel(const double2 *__restrict__ p
 	}
 }
 
-__global__ void grid2_kernel(const double4 *__restrict__ part, int nb, int side, double eps, Grid2 *__restrict__ g)
+__global__ void __launch_bounds__(kB) grid2_kernel(const double4 *__restrict__ part, int nb, int side, double eps, Grid2 *__restrict__ g)
 {
-	double4 r = part[0];
-	for (int k = 1; k < nb; ++k) { r.x = fmin(r.x, part[k].x); r.y = fmin(r.y, part[k].y); r.z = fmax(r.z, part[k].z); r.w = fmax(r.w, part[k].w); }
+	double lx = INFINITY, ly = INFINITY, hx = -INFINITY, hy = -INFINITY;
+	for (int k = threadIdx.x; k < nb; k += kB)
+	{
+		const double4 v = part[k];
+		lx = fmin(lx, v.x); ly = fmin(ly, v.y); hx = fmax(hx, v.z); hy = fmax(hy, v.w);
+	}
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		lx = fmin(lx, __shfl_down_sync(0xffffffffu, lx, o)); ly = fmin(ly, __shfl_down_sync(0xffffffffu, ly, o));
+		hx = fmax(hx, __shfl_down_sync(0xffffffffu, hx, o)); hy = fmax(hy, __shfl_down_sync(0xffffffffu, hy, o));
+	}
+	__shared__ double4 sh[kB / 32];
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = make_double4(lx, ly, hx, hy);
+	__syncthreads();
+	if (threadIdx.x != 0) return;
+	double4 r = sh[0];
+	for (int k = 1; k < kB / 32; ++k) { r.x = fmin(r.x, sh[k].x); r.y = fmin(r.y, sh[k].y); r.z = fmax(r.z, sh[k].z); r.w = fmax(r.w, sh[k].w); }
 	double delta = __ddiv_rn(fmax(__dsub_rn(r.z, r.x), __dsub_rn(r.w, r.y)), (double)side);
 	if (delta < eps) delta = eps;
 	g->minx = r.x; g->miny = r.y; g->rdelta = __ddiv_rn(1.0, delta); g->pad = delta;
@@ -146,12 +188,12 @@ __global__ void __launch_bounds__(kB) keys2_kernel(const double2 *__restrict__ p
 }
 
 // ---------------------------------------------------------------------------------------------
-//  stable LSD radix sort of (key, id) pairs; digit of `bits` <= 8 bits per pass
+//  stable LSD radix sort of (key, id) pairs; digit of `bits` <= kRsBits bits per pass
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kB) rs_hist_kernel(const u32 *__restrict__ keys, int64_t n, int shift, int bits,
                                                      u32 *__restrict__ hist, int ntiles)
 {
-	__shared__ u32 h[256];
+	__shared__ u32 h[kRsBins];
 	const int bins = 1 << bits;
 	const u32 mask = (u32)bins - 1u;
 	for (int t = threadIdx.x; t < bins; t += kB) h[t] = 0;
@@ -167,37 +209,61 @@ __global__ void __launch_bounds__(kB) rs_hist_kernel(const u32 *__restrict__ key
 	for (int t = threadIdx.x; t < bins; t += kB) hist[(size_t)t * ntiles + blockIdx.x] = h[t];
 }
 
-// exclusive scan of `total` counters in place (one CTA; total = bins * tiles is small)
-__global__ void __launch_bounds__(1024) rs_scan_kernel(u32 *__restrict__ hist, int total)
+// hist[d][tile] -> exclusive prefix over the tiles of digit d (in place), tot[d] = count of digit d.
+// One CTA per digit; the rows are contiguous.
+__global__ void __launch_bounds__(kB) rs_scan_kernel(u32 *__restrict__ hist, int ntiles, u32 *__restrict__ tot)
 {
-	__shared__ u32 part[1024];
-	const int per = (total + 1023) / 1024;
-	const int b = min(threadIdx.x * per, total), e = min(b + per, total);
-	u32 s = 0;
-	for (int i = b; i < e; ++i) s += hist[i];
-	part[threadIdx.x] = s;
+	__shared__ u32 wsum[kB / 32];
+	__shared__ u32 carry;
+	u32 *row = hist + (size_t)blockIdx.x * ntiles;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	if (threadIdx.x == 0) carry = 0;
 	__syncthreads();
-	for (int o = 1; o < 1024; o <<= 1)
+	for (int base = 0; base < ntiles; base += kB)
 	{
-		u32 v = (threadIdx.x >= o) ? part[threadIdx.x - o] : 0u;
+		const int i = base + threadIdx.x;
+		const u32 v = (i < ntiles) ? row[i] : 0u;
+		u32 x = v;
+		for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+		if (lane == 31) wsum[w] = x;
 		__syncthreads();
-		part[threadIdx.x] += v;
+		u32 off = carry;
+		for (int k = 0; k < w; ++k) off += wsum[k];
+		if (i < ntiles) row[i] = off + x - v;
+		__syncthreads();
+		if (threadIdx.x == kB - 1) carry = off + x;
 		__syncthreads();
 	}
-	u32 run = part[threadIdx.x] - s;
-	for (int i = b; i < e; ++i) { const u32 v = hist[i]; hist[i] = run; run += v; }
+	if (threadIdx.x == 0) tot[blockIdx.x] = carry;
 }
 
 // Every warp owns kRsItems*32 consecutive keys of the tile and ranks them in order: stable.
 __global__ void __launch_bounds__(kB) rs_scatter_kernel(const u32 *__restrict__ keys_in, const u32 *__restrict__ ids_in,
                                                         u32 *__restrict__ keys_out, u32 *__restrict__ ids_out, int64_t n,
-                                                        int shift, int bits, const u32 *__restrict__ hist, int ntiles)
+                                                        int shift, int bits, const u32 *__restrict__ hist, int ntiles,
+                                                        const u32 *__restrict__ tot)
 {
-	__shared__ u32 wh[kB / 32][256];
+	__shared__ u32 wh[kB / 32][kRsBins];
+	__shared__ u32 dbase[kRsBins];
+	__shared__ u32 wtot[kB / 32];
 	const int bins = 1 << bits;
 	const u32 mask = (u32)bins - 1u;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	for (int t = threadIdx.x; t < (kB / 32) * 256; t += kB) (&wh[0][0])[t] = 0;
+	for (int t = threadIdx.x; t < (kB / 32) * kRsBins; t += kB) (&wh[0][0])[t] = 0;
+	// exclusive scan of the digit totals (bins <= 2 * kB): every thread owns two consecutive digits
+	{
+		const int d0 = 2 * threadIdx.x;
+		const u32 a = (d0 < bins) ? tot[d0] : 0u, b = (d0 + 1 < bins) ? tot[d0 + 1] : 0u;
+		u32 x = a + b;
+		for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+		if (lane == 31) wtot[warp] = x;
+		__syncthreads();
+		u32 off = 0;
+		for (int k = 0; k < warp; ++k) off += wtot[k];
+		const u32 ex = off + x - (a + b);
+		if (d0 < bins) dbase[d0] = ex;
+		if (d0 + 1 < bins) dbase[d0 + 1] = ex + a;
+	}
 	__syncthreads();
 	const int64_t base = (int64_t)blockIdx.x * kRsTile + (int64_t)warp * (kRsItems * 32);
 	u32 key[kRsItems];
@@ -211,7 +277,7 @@ __global__ void __launch_bounds__(kB) rs_scatter_kernel(const u32 *__restrict__ 
 	__syncthreads();
 	for (int d = threadIdx.x; d < bins; d += kB)
 	{
-		u32 run = hist[(size_t)d * ntiles + blockIdx.x];
+		u32 run = dbase[d] + hist[(size_t)d * ntiles + blockIdx.x];
 #pragma unroll
 		for (int w = 0; w < kB / 32; ++w) { const u32 c = wh[w][d]; wh[w][d] = run; run += c; }
 	}
@@ -376,70 +442,88 @@ __global__ void __launch_bounds__(kB) m2m2_kernel(Tree2 t, int l)
 //  M2L of level l (fmm_c2c2, fmm_cart.cuh:214-262) fused with the L2L from level l-1
 //  (fmm_pushl, :288-334): thread per node of level l, each node's local written once.
 // ---------------------------------------------------------------------------------------------
-template <int P>
+template <int P, int LANES>
 __global__ void __launch_bounds__(128) m2l_l2l2_kernel(Tree2 t, int l, int radius, double eps2)
+// LANES lanes share one target node and split its source cells (LANES = 32 on the small levels, where a
+// thread per node would serialise ~27 dependent M2L evaluations on a nearly empty machine)
 {
 	const int sl = 1 << l;
-	const int ij = blockIdx.x * 128 + threadIdx.x;
-	if (ij >= sl * sl) return;
+	const int gt = blockIdx.x * 128 + threadIdx.x;
+	const int ij = gt / LANES, sub = gt % LANES;
+	const bool live = ij < sl * sl;
 	const int i = ij >> l, j = ij & (sl - 1);
 	const int beg = tbeg(l), node = beg + ij;
-	const double2 ct = t.center[node];
+	double2 ct = make_double2(0.0, 0.0);
 	double2 Lo[P + 1];
 #pragma unroll
 	for (int n = 0; n <= P; ++n) Lo[n] = make_double2(0.0, 0.0);
+	const bool nonempty = live && t.mult[node] > 0;
+	if (live) ct = t.center[node];
 
-	if (t.mult[node] > 0)
+	if (nonempty)
 	{
 		const int im = (i >> 1) << 1, jm = (j >> 1) << 1;
 		const int kmin = max(im - 2 * radius, 0), kmax = min(im + 2 * radius + 1, sl - 1);
 		const int gmin = max(jm - 2 * radius, 0), gmax = min(jm + 2 * radius + 1, sl - 1);
-		for (int k = kmin; k <= kmax; ++k)
-			for (int g = gmin; g <= gmax; ++g)
+		const int gw = gmax - gmin + 1, ncand = (kmax - kmin + 1) * gw;
+		for (int c = sub; c < ncand; c += LANES)
+		{
+			const int k = kmin + c / gw, g = gmin + c % gw;
+			if (!(k > i + radius || k < i - radius || g > j + radius || g < j - radius)) continue;
+			const int s = beg + k * sl + g;
+			if (t.mult[s] <= 0) continue; // an empty source has Z = 0
+			const double2 cs = t.center[s];
+			const double dx = ct.x - cs.x, dy = ct.y - cs.y;
+			// The reference normalises by r = sqrt(|dz|^2 + eps2) (fmm_cart.cuh:241-249), so its direction
+			// d = dz / r is not a unit vector and its gradient tuple is the Chebyshev pair
+			// g_m = (-1)^m (m-1)! r^-m (T_m(d0), d1 U_(m-1)(d0)); both obey E_(m+1) = 2 d0 E_m - E_(m-1).
+			const double r2 = dx * dx + dy * dy + eps2;
+			const double ri = rsqrt(r2);
+			const double d0 = dx * ri, d1 = dy * ri, two_d0 = 2.0 * d0;
+			double2 G[2 * P + 1];
+			G[0] = make_double2(0.0, 0.0);
 			{
-				if (!(k > i + radius || k < i - radius || g > j + radius || g < j - radius)) continue;
-				const int s = beg + k * sl + g;
-				if (t.mult[s] <= 0) continue; // an empty source has Z = 0
-				const double2 cs = t.center[s];
-				const double dx = ct.x - cs.x, dy = ct.y - cs.y;
-				// The reference normalises by r = sqrt(|dz|^2 + eps2) (fmm_cart.cuh:241-249), so its direction
-				// d = dz / r is not a unit vector and its gradient tuple is the Chebyshev pair
-				// g_m = (-1)^m (m-1)! r^-m (T_m(d0), d1 U_(m-1)(d0)); both obey E_(m+1) = 2 d0 E_m - E_(m-1).
-				const double r2 = dx * dx + dy * dy + eps2;
-				const double r = sqrt(r2), ri = 1.0 / r;
-				const double d0 = dx / r, d1 = dy / r, two_d0 = 2.0 * d0;
-				double2 G[2 * P + 1];
-				G[0] = make_double2(0.0, 0.0);
+				double2 Em = make_double2(1.0, 0.0), E = make_double2(d0, d1);
+				double sc = -ri; // (-1)^m (m-1)! r^-m
+				G[1] = make_double2(sc * E.x, sc * E.y);
+#pragma unroll
+				for (int mm = 2; mm <= 2 * P; ++mm)
 				{
-					double2 Em = make_double2(1.0, 0.0), E = make_double2(d0, d1);
-					double sc = -ri; // (-1)^m (m-1)! r^-m
-					G[1] = make_double2(sc * E.x, sc * E.y);
-#pragma unroll
-					for (int mm = 2; mm <= 2 * P; ++mm)
-					{
-						const double2 En = make_double2(fma(two_d0, E.x, -Em.x), fma(two_d0, E.y, -Em.y));
-						Em = E; E = En;
-						sc *= -(double)(mm - 1) * ri;
-						G[mm] = make_double2(sc * E.x, sc * E.y);
-					}
-				}
-				const double2 *zs = t.Z + (size_t)s * (P + 1);
-#pragma unroll
-				for (int q = 0; q <= P; ++q)
-				{
-					if (q == 1) continue; // the dipole about the centre of charge is identically 0
-					const double2 Zq = zs[q];
-#pragma unroll
-					for (int n = 0; n <= P; ++n)
-						if (n + q >= 1) cfma_conj(Lo[n], Zq, G[n + q]);
+					const double2 En = make_double2(fma(two_d0, E.x, -Em.x), fma(two_d0, E.y, -Em.y));
+					Em = E; E = En;
+					sc *= -(double)(mm - 1) * ri;
+					G[mm] = make_double2(sc * E.x, sc * E.y);
 				}
 			}
+			const double2 *zs = t.Z + (size_t)s * (P + 1);
 #pragma unroll
-		for (int n = 2; n <= P; ++n)
-		{
-			const double f = 1.0 / fact_c(n);
-			Lo[n].x *= f; Lo[n].y *= f;
+			for (int q = 0; q <= P; ++q)
+			{
+				if (q == 1) continue; // the dipole about the centre of charge is identically 0
+				const double2 Zq = zs[q];
+#pragma unroll
+				for (int n = 0; n <= P; ++n)
+					if (n + q >= 1) cfma_conj(Lo[n], Zq, G[n + q]);
+			}
 		}
+	}
+	if (LANES > 1)
+	{
+#pragma unroll
+		for (int n = 0; n <= P; ++n)
+#pragma unroll
+			for (int o = LANES / 2; o > 0; o >>= 1)
+			{
+				Lo[n].x += __shfl_xor_sync(0xffffffffu, Lo[n].x, o);
+				Lo[n].y += __shfl_xor_sync(0xffffffffu, Lo[n].y, o);
+			}
+	}
+	if (!live || sub != 0) return;
+#pragma unroll
+	for (int n = 2; n <= P; ++n)
+	{
+		const double f = 1.0 / fact_c(n);
+		Lo[n].x *= f; Lo[n].y *= f;
 	}
 	if (l > 2)
 	{
@@ -492,16 +576,10 @@ __global__ void __launch_bounds__(kB) near_l2p2_kernel(Tree2 t, const double2 *_
 		for (int k = kmin; k <= kmax; ++k)
 		{
 			const int b = t.lindex[k * side + lmin], e = t.lindex[k * side + lmax + 1];
-#pragma unroll 4
-			for (int s = b; s < e; ++s)
-			{
-				const double2 q = __ldg(sp + s);
-				const double dx = p.x - q.x, dy = p.y - q.y;
-				const double r2 = fma(dy, dy, fma(dx, dx, eps2));
-				const double inv = rcp_nr(r2);
-				ax = fma(inv, dx, ax);
-				ay = fma(inv, dy, ay);
-			}
+			int s = b;
+			for (; s + 4 <= e; s += 4)
+				pair4(p.x, p.y, __ldg(sp + s), __ldg(sp + s + 1), __ldg(sp + s + 2), __ldg(sp + s + 3), eps2, ax, ay);
+			for (; s < e; ++s) pair1(p.x, p.y, __ldg(sp + s), eps2, ax, ay);
 		}
 	}
 	// L2P: f = -sum_n n L_n conj(d)^(n-1), Horner from the top
@@ -555,19 +633,18 @@ __global__ void __launch_bounds__(kB) direct2_kernel(const double2 *__restrict__
 			sm[k] = (tile + k < n) ? p[tile + k] : make_double2(0.0, 0.0);
 		__syncthreads();
 		const int cnt = (int)min((int64_t)kDTile, n - tile);
-#pragma unroll 2
-		for (int j = 0; j < cnt; ++j)
+		int j = 0;
+		for (; j + 4 <= cnt; j += 4)
+		{
+			const double2 q0 = sm[j], q1 = sm[j + 1], q2 = sm[j + 2], q3 = sm[j + 3];
+#pragma unroll
+			for (int u = 0; u < IPT; ++u) pair4(pi[u].x, pi[u].y, q0, q1, q2, q3, eps2, ax[u], ay[u]);
+		}
+		for (; j < cnt; ++j)
 		{
 			const double2 q = sm[j];
 #pragma unroll
-			for (int u = 0; u < IPT; ++u)
-			{
-				const double dx = pi[u].x - q.x, dy = pi[u].y - q.y;
-				const double r2 = fma(dy, dy, fma(dx, dx, eps2));
-				const double inv = rcp_nr(r2);
-				ax[u] = fma(inv, dx, ax[u]);
-				ay[u] = fma(inv, dy, ay[u]);
-			}
+			for (int u = 0; u < IPT; ++u) pair1(pi[u].x, pi[u].y, q, eps2, ax[u], ay[u]);
 		}
 	}
 	const double s = param ? param[0] : 1.0;
@@ -736,6 +813,12 @@ int fmm2_levels(int64_t n, int order, double dens)
 }
 
 static double eps2_of(const nbco_ctx *ctx) { return ctx->cfg.eps2_d > 0.0 ? ctx->cfg.eps2_d : (double)ctx->cfg.eps2; }
+// the near field multiplies four softened squared distances before taking one reciprocal
+static int check_eps2(double eps2)
+{
+	if (!(eps2 >= 1.e-70)) { set_error("2D path: eps2 = %g is below 1e-70 (products of four squared distances would underflow)", eps2); return NBCO_ERR_INVALID; }
+	return NBCO_OK;
+}
 
 template <int P>
 static void run_order(nbco_ctx *ctx, Fmm2Plan &pl, Tree2 t, double2 *d_pos, double2 *d_acc, int64_t n, const double *d_param,
@@ -756,7 +839,8 @@ static void run_order(nbco_ctx *ctx, Fmm2Plan &pl, Tree2 t, double2 *d_pos, doub
 	for (int l = 2; l <= L; ++l)
 	{
 		const int cnt = 1 << (2 * l);
-		m2l_l2l2_kernel<P><<<(cnt + 127) / 128, 128, 0, st>>>(t, l, radius, eps2);
+		if (l <= 7) m2l_l2l2_kernel<P, 32><<<(cnt * 32 + 127) / 128, 128, 0, st>>>(t, l, radius, eps2);
+		else m2l_l2l2_kernel<P, 1><<<(cnt + 127) / 128, 128, 0, st>>>(t, l, radius, eps2);
 		ctx->launches++;
 	}
 	cudaEventRecord(pl.ev[P2_NEAR_L2P], st);
@@ -772,6 +856,7 @@ int fmm2_launch(nbco_ctx *ctx, double *d_pos, double *d_acc, int64_t n, const do
 	if (n > 0x7FFFFFF0LL) { set_error("fmm2: n too large"); return NBCO_ERR_INVALID; }
 	const int P = ctx->cfg.order;
 	if (P < 1 || P > kMaxP2) { set_error("fmm2: order %d outside 1..%d", P, kMaxP2); return NBCO_ERR_INVALID; }
+	NBCO_TRY(check_eps2(eps2_of(ctx)));
 	const int radius = (int)ctx->cfg.radius; // int radius = tree_radius (fmm_cart.cuh:398)
 	if (radius < 1) { set_error("fmm2: radius must be >= 1"); return NBCO_ERR_INVALID; }
 	if (!ctx->fmm2) ctx->fmm2 = new Fmm2Plan();
@@ -782,11 +867,11 @@ int fmm2_launch(nbco_ctx *ctx, double *d_pos, double *d_acc, int64_t n, const do
 	const int side = 1 << L, m = side * side;
 	const int64_t ntot = (((int64_t)1 << (2 * (L + 1))) - 1) / 3;
 	const int ntiles = (int)((n + kRsTile - 1) / kRsTile);
-	const int nbits = 2 * L, npass = (nbits + 7) / 8, bits = (nbits + npass - 1) / npass;
+	const int nbits = 2 * L, npass = (nbits + kRsBits - 1) / kRsBits, bits = (nbits + npass - 1) / npass;
 	const int nbb = grid_for(n, kB, ctx->sm_count, 8);
 	NBCO_TRY(pl.keysA.reserve(4 * (size_t)n)); NBCO_TRY(pl.keysB.reserve(4 * (size_t)n));
 	NBCO_TRY(pl.idsA.reserve(4 * (size_t)n)); NBCO_TRY(pl.idsB.reserve(4 * (size_t)n));
-	NBCO_TRY(pl.hist.reserve(4 * (size_t)ntiles * 256));
+	NBCO_TRY(pl.hist.reserve(4 * ((size_t)ntiles + 1) * kRsBins));
 	NBCO_TRY(pl.tmp.reserve(32 * (size_t)n));
 	NBCO_TRY(pl.part.reserve(32 * (size_t)nbb));
 	NBCO_TRY(pl.grid.reserve(sizeof(Grid2)));
@@ -805,7 +890,7 @@ int fmm2_launch(nbco_ctx *ctx, double *d_pos, double *d_acc, int64_t n, const do
 
 	NBCO_CUDA(cudaEventRecord(pl.ev[P2_KEYS], st));
 	bbox2_kernel<<<nbb, kB, 0, st>>>(pos, n, pl.part.as<double4>());
-	grid2_kernel<<<1, 1, 0, st>>>(pl.part.as<double4>(), nbb, side, std::sqrt(eps2_of(ctx)), pl.grid.as<Grid2>());
+	grid2_kernel<<<1, kB, 0, st>>>(pl.part.as<double4>(), nbb, side, std::sqrt(eps2_of(ctx)), pl.grid.as<Grid2>());
 	keys2_kernel<<<nbb, kB, 0, st>>>(pos, n, pl.grid.as<Grid2>(), side, pl.keysA.as<u32>());
 	ctx->launches += 3;
 
@@ -815,8 +900,9 @@ int fmm2_launch(nbco_ctx *ctx, double *d_pos, double *d_acc, int64_t n, const do
 	{
 		const int shift = pass * bits, b = std::min(bits, nbits - shift);
 		rs_hist_kernel<<<ntiles, kB, 0, st>>>(kin, n, shift, b, pl.hist.as<u32>(), ntiles);
-		rs_scan_kernel<<<1, 1024, 0, st>>>(pl.hist.as<u32>(), (1 << b) * ntiles);
-		rs_scatter_kernel<<<ntiles, kB, 0, st>>>(kin, pass == 0 ? nullptr : iin, kout, iout, n, shift, b, pl.hist.as<u32>(), ntiles);
+		u32 *tot = pl.hist.as<u32>() + (size_t)ntiles * kRsBins;
+		rs_scan_kernel<<<1 << b, kB, 0, st>>>(pl.hist.as<u32>(), ntiles, tot);
+		rs_scatter_kernel<<<ntiles, kB, 0, st>>>(kin, pass == 0 ? nullptr : iin, kout, iout, n, shift, b, pl.hist.as<u32>(), ntiles, tot);
 		ctx->launches += 3;
 		std::swap(kin, kout); std::swap(iin, iout);
 	}
@@ -873,6 +959,7 @@ int direct2_launch(nbco_ctx *ctx, const double *d_pos, double *d_acc, int64_t n,
 	const int64_t cnt = ie - ib;
 	if (cnt <= 0) return NBCO_OK;
 	const double eps2 = eps2_of(ctx);
+	NBCO_TRY(check_eps2(eps2));
 	// two targets per thread once there are enough targets to fill the machine twice
 	if (cnt >= (int64_t)ctx->sm_count * kB * 4)
 	{
