@@ -237,6 +237,9 @@ def run_ours(args):
     # secondary metric (BASELINE config 3): O(N^2) direct sum, targets sharded over the ranks
     direct = bench_direct(nb, torch, dist, local, peaks, rank, world) if args.direct else None
 
+    # secondary metric (BASELINE config 4): 2D fp64 FMM under PEFRL, one GPU
+    fmm2d = bench_fmm2d(nb, torch, local) if (args.fmm2d and world == 1) else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -291,6 +294,8 @@ def run_ours(args):
     }
     if direct is not None:
         out["direct_sum"] = direct
+    if fmm2d is not None:
+        out["fmm2d"] = fmm2d
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -339,6 +344,74 @@ def bench_direct(nb, torch, dist, local, peaks, rank, world, n=1 << 20):
     return {"n": n, "n_gpus": world, "ms": best, "Ginteractions_per_s": inter / 1e9,
             "roofline": {"bound": "fp32_fma", "achieved": inter * 18 / 1e12, "peak": peak, "unit": "TFLOP/s",
                          "frac": inter * 18 / 1e12 / peak, "flop_per_interaction": 18}}
+
+
+FP64_DFMA_PEAK = 17.1e12   # DFMA/s, measured on this pool's B200 with tools/dfma_peak.cu (profiles/r01_notes.md)
+
+
+def bench_fmm2d(nb, torch, local, n=1 << 22, order=5, steps=4):
+    """secondary metric (BASELINE config 4): 2D fp64 FMM (uniform grid, p = 5) under PEFRL, N = 4M, KV beam of
+    main.cu.  One PEFRL step = 4 force evaluations + 5 streaming passes.  Roofline of the dominant kernel
+    (near field + L2P): FP64 pipe, 9.75 DP instructions per pair interaction (4 pairs share one reciprocal)."""
+    st = nb.init_kv2(n)
+    par = nb.default_param2(n)
+    ctx = nb.Context(device=local, order=order)
+    buf = torch.from_numpy(np.concatenate([st[0], st[1], np.zeros((n, 2))])).cuda()
+    dpar = torch.from_numpy(par).cuda()
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    ev = nb.EVAL_COULOMB_FMM2
+    ctx.compute_force2(ev, buf.data_ptr(), n, dpar.data_ptr())
+    ctx.integrate2(nb.PEFRL, ev, buf.data_ptr(), n, dpar.data_ptr(), 5e-4, 1)
+    l0 = ctx.fmm2_info().kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    ctx.integrate2(nb.PEFRL, ev, buf.data_ptr(), n, dpar.data_ptr(), 5e-4, steps)
+    e1.record(stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    info = ctx.fmm2_info()
+    ph = ctx.fmm2_phase_ms()          # phases of the last evaluation
+    T = ctx.fmm2_tree()
+    side = 1 << info.levels
+    mm = T["mult"][(4 ** info.levels - 1) // 3:].reshape(side, side).astype(np.int64)
+    pad = np.pad(mm, 1)
+    inter = int((mm * sum(pad[1 + a:1 + a + side, 1 + b:1 + b + side] for a in (-1, 0, 1) for b in (-1, 0, 1))).sum())
+    near_ms = ph["near_l2p"]
+    dp = inter * 9.75 / (near_ms * 1e-3)
+    # e2e: host state through nbco_step_host2 (H2D [pos|vel|acc], one PEFRL step, D2H), pinned memory
+    hb = torch.empty(6 * n, dtype=torch.float64).pin_memory()
+    hb.copy_(buf.cpu().reshape(-1))
+    ctx.step_host2(nb.PEFRL, ev, hb.numpy(), n, par, 5e-4, 1)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        ctx.step_host2(nb.PEFRL, ev, hb.numpy(), n, par, 5e-4, 1)
+    te = (time.perf_counter() - t0) / 2
+    cpu = None
+    try:
+        from refs2d import Ref2
+        if Ref2.available():
+            ns, threads = 1 << 19, min(os.cpu_count() or 1, 64)
+            s2 = nb.init_kv2(ns)
+            p2 = nb.default_param2(ns)
+            b2 = np.concatenate([s2[0], s2[1], np.zeros((ns, 2))]).copy()
+            ref = Ref2(order=order, threads=threads)
+            ref.eval(3, b2, ns, p2)
+            t0 = time.perf_counter()
+            ref.integrate(3, 3, b2, ns, p2, 5e-4, 1)
+            tc = time.perf_counter() - t0
+            cpu = {"value": ns / tc, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
+                   "sample": f"1 PEFRL step (4 evaluations of coulombOscillatorFMM_cpu) at N={ns}, p={order}, {tc:.1f} s"}
+    except Exception as e:  # the checker is optional here
+        cpu = {"error": str(e)}
+    return {"metric": "2D fp64 FMM particle-steps/s (PEFRL)", "n": n, "order": order, "levels": int(info.levels),
+            "value": n * steps / (ms * 1e-3), "ms_per_step": ms / steps, "evals_per_step": 4, "dtype": "f64",
+            "phases_ms_last_eval": {k: round(v, 4) for k, v in ph.items()},
+            "roofline": {"bound": "fp64_fma", "kernel": "near_l2p2_kernel", "achieved": dp / 1e12, "peak": FP64_DFMA_PEAK / 1e12,
+                         "unit": "T DP-instr/s", "frac": dp / FP64_DFMA_PEAK, "pair_interactions": inter,
+                         "dp_instr_per_interaction": 9.75, "avg_launch_ms": near_ms},
+            "e2e": {"value": n / te, "unit": "particle-steps/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n},
+            "gpu_launches": int(info.kernel_launches - l0), "cpu_baseline": cpu}
 
 
 def cpu_baseline(n, order, m2l_first, bounded, steps=None, warmup=0):
@@ -407,6 +480,7 @@ def main():
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--m2l-first", dest="m2l_first", type=int, default=1)
     ap.add_argument("--no-direct", dest="direct", action="store_false")
+    ap.add_argument("--no-fmm2d", dest="fmm2d", action="store_false")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
