@@ -46,6 +46,7 @@ SYMBOLS = [
     "nbco_compute_force2", "nbco_integrate2", "nbco_mean_rel_err2", "nbco_energy2", "nbco_run_host2", "nbco_step_host2",
     "nbco_fmm2_levels", "nbco_fmm2_get_info", "nbco_fmm2_get_tree", "nbco_fmm2_get_phase_ms",
     "nbco_init_ga2", "nbco_init_kv2", "nbco_beam_params2", "nbco_state_read2", "nbco_state_write2",
+    "nbco_peer_export", "nbco_peer_attach", "nbco_peer_commit", "nbco_peer_barrier", "nbco_peer_gather", "nbco_peer_detach",
     "nbco_shard_range", "nbco_init_ga", "nbco_init_test_cube", "nbco_state_read", "nbco_state_write", "nbco_free",
 ]
 
@@ -89,6 +90,12 @@ def _load():
     L.nbco_state_read.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(i64)]
     L.nbco_state_write.argtypes = [C.c_char_p, vp, i64]
     L.nbco_free.argtypes = [vp]
+    L.nbco_peer_export.argtypes = [vp, i64, vp]
+    L.nbco_peer_attach.argtypes = [vp, C.c_int32, vp]
+    L.nbco_peer_commit.argtypes = [vp]
+    L.nbco_peer_barrier.argtypes = [vp]
+    L.nbco_peer_gather.argtypes = [vp, vp, i64]
+    L.nbco_peer_detach.argtypes = [vp]
     # 2D fp64 path
     for f in ("nbco_force_direct2", "nbco_force_fmm2", "nbco_coulomb_direct2", "nbco_coulomb_fmm2", "nbco_add_elastic2"):
         getattr(L, f).argtypes = [vp, vp, vp, i64, vp]
@@ -322,6 +329,27 @@ class Context:
         ev = (C.c_int64 * 2)()
         k = lib.nbco_fmm_phase_totals(self._h, names, ms, 32, ev, 1 if reset else 0)
         return {names[j].decode(): ms[j] for j in range(k)}, ev[0], ev[1]
+
+    # ---- multi-GPU over peer memory ----
+    def peer_export(self, n):
+        h = np.zeros(192, np.uint8)
+        _check(lib.nbco_peer_export(self._h, n, _hp(h)))
+        return h
+
+    def peer_attach(self, rank, handles):
+        _check(lib.nbco_peer_attach(self._h, rank, _hp(np.ascontiguousarray(handles, np.uint8))))
+
+    def peer_commit(self):
+        _check(lib.nbco_peer_commit(self._h))
+
+    def peer_barrier(self):
+        _check(lib.nbco_peer_barrier(self._h))
+
+    def peer_gather(self, d_buf, n):
+        _check(lib.nbco_peer_gather(self._h, d_buf, n))
+
+    def peer_detach(self):
+        _check(lib.nbco_peer_detach(self._h))
 
     # ---- 2D fp64 path ----
     def force_direct2(self, d_pos, d_acc, n, d_param=None):

@@ -128,6 +128,7 @@ static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int
 // same fma sequence per element as integrator.cuh:68-96 applied step by step, in fewer passes.
 static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64_t n, const float *param, float dtf, int64_t nsteps)
 {
+	if (ctx->peer.active && scheme != NBCO_LEAPFROG) { set_error("peer mode integrates with the leapfrog scheme only"); return NBCO_ERR_INVALID; }
 	if (scheme != NBCO_LEAPFROG || nsteps <= 0)
 	{
 		for (int64_t s = 0; s < nsteps; ++s)
@@ -137,12 +138,16 @@ static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64
 	float *pos = buf, *vel = buf + 3*n, *acc = buf + 6*n;
 	const long double dt = dtf;
 	const float h = (float)(dt * 1.0L * 0.5L);
+	// peer mode (peer.cu): every rank steps its own tree-order range; the evaluator exchanges what it needs
+	int64_t lo = 0, hi = n;
+	const bool fmm = evaluator == NBCO_EVAL_FMM3_KD || evaluator == NBCO_EVAL_COULOMB_FMM3_KD;
+	if (ctx->peer.active && fmm) nbco_shard_range(n, ctx->cfg.rank, ctx->cfg.world, &lo, &hi);
 	for (int64_t s = 0; s < nsteps; ++s)
 	{
-		NBCO_TRY(kick_drift_launch(ctx, pos, vel, acc, h, h, s > 0, dtf, n));
+		NBCO_TRY(kick_drift_launch(ctx, pos + 3*lo, vel + 3*lo, acc + 3*lo, h, h, s > 0, dtf, hi - lo));
 		NBCO_TRY(eval_dispatch(ctx, evaluator, pos, acc, n, param));
 	}
-	return step_launch(ctx, vel, acc, h, n);
+	return step_launch(ctx, vel + 3*lo, acc + 3*lo, h, hi - lo);
 }
 
 } // namespace nbco
@@ -201,6 +206,7 @@ void nbco_destroy(nbco_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->cfg.device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	peer_release(ctx);
 	fmm3_destroy(ctx);
 	fmm2_destroy(ctx);
 	ctx->pos4.release(); ctx->red.release(); ctx->h_state.release(); ctx->h_param.release();

@@ -42,6 +42,22 @@ struct DevBuf
 };
 
 struct FmmPlan; // fmm3.cu
+
+// Multi-GPU over peer memory (peer.cu): what this rank publishes and what it has mapped from the others.
+constexpr int kPeerMax = 8;
+constexpr size_t kPeerHeader = 1024; // bytes of flag words at the start of the published buffer
+struct PeerState
+{
+	bool active = false;
+	int world = 1, me = 0;
+	int64_t n = 0;
+	DevBuf pub;                       // [flags | tree-ordered positions 12 n | velocities 12 n]
+	void *center[kPeerMax] = {}, *mpole[kPeerMax] = {}, *pubp[kPeerMax] = {}; // [me] = local
+	bool opened[kPeerMax] = {};
+	unsigned long long epoch = 0;     // barriers passed so far (identical on every rank)
+	bool have_full = true;            // the caller's arrays hold ALL positions / velocities (first evaluation)
+	float barrier_ms = 0.f;
+};
 struct Fmm2Plan; // fmm2.cu
 
 } // namespace nbco
@@ -63,6 +79,7 @@ struct nbco_ctx
 	void *pinned = nullptr; size_t pinned_bytes = 0;
 
 	nbco::FmmPlan *fmm = nullptr;
+	nbco::PeerState peer;
 	nbco::Fmm2Plan *fmm2 = nullptr;
 };
 
@@ -80,6 +97,12 @@ int kinetic_elastic_launch(nbco_ctx *ctx, const float *d_buf, int64_t n, const f
 // fmm3.cu
 int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const float *d_param, bool fuse_elastic);
 void fmm3_destroy(nbco_ctx *ctx);
+// peer.cu
+int peer_barrier(nbco_ctx *ctx);                                           // all ranks, on the context streams
+int peer_publish(nbco_ctx *ctx, const float *d_full, int which, int64_t n);  // own range of pos (0) / vel (1) -> published mirror
+int peer_pull(nbco_ctx *ctx, float *d_full, int which, int64_t n);           // the other ranks' ranges <- their mirrors
+void peer_release(nbco_ctx *ctx);
+int fmm3_peer_buffers(nbco_ctx *ctx, int64_t n, void **center, void **mpole); // fmm3.cu: plans, returns the node arrays
 // fmm2.cu (2D fp64 path)
 int fmm2_launch(nbco_ctx *ctx, double *d_pos, double *d_acc, int64_t n, const double *d_param, bool fuse_elastic);
 int direct2_launch(nbco_ctx *ctx, const double *d_pos, double *d_acc, int64_t n, const double *d_param);

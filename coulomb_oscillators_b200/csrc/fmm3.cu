@@ -58,7 +58,10 @@ struct TravArgs
 	int ntot, L, m2l_first;
 	float radius;
 	int64_t sh_lo, sh_hi; // particles (tree order) whose accelerations this rank computes
+	PeerTab peers;        // centres of remote nodes are read from their owners
 };
+
+__device__ __forceinline__ float4 trav_center(const TravArgs &a, int node) { return a.peers.center[node_owner(a.peers, node)][node]; }
 
 __device__ __forceinline__ int node_mult(int64_t n, int node, int &level)
 {
@@ -78,7 +81,7 @@ __device__ __forceinline__ bool node_mine(const TravArgs &a, int node)
 // kd_admissible (:401-414) with the host's operation order; pow() comes from the host table
 __device__ __forceinline__ bool mac_ok(const TravArgs &a, int n1, int n2)
 {
-	float4 c1 = a.center[n1], c2 = a.center[n2];
+	float4 c1 = trav_center(a, n1), c2 = trav_center(a, n2);
 	float dx = __fsub_rn(c2.x, c1.x), dy = __fsub_rn(c2.y, c1.y), dz = __fsub_rn(c2.z, c1.z);
 	float dist2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 	float sz = fmaxf(c1.w, c2.w);
@@ -112,19 +115,20 @@ __device__ __forceinline__ u32 warp_append(u32 *counter, int count)
 // returns 0 nothing, 1 p2p, 2 m2l, 3 self split, 4 split y, 5 split x; flags = which side is a target here
 __device__ __forceinline__ int classify_pair(const TravArgs &a, int2 np, int &flags)
 {
+	// bit 0: np.x is a target of this rank, bit 1: np.y is; untouched pairs (and their descendants) are
+	// dropped before any node data is read.  With one rank every node is a target (flags = 3).
+	flags = (node_mine(a, np.x) ? 1 : 0) | (node_mine(a, np.y) ? 2 : 0);
+	if (!flags) return 0;
 	int kind;
 	const bool xl = 2*np.x + 1 >= a.ntot, yl = 2*np.y + 1 >= a.ntot;
 	if (!a.m2l_first && xl && yl) kind = (np.x != np.y) ? 1 : 0;
 	else if (np.x == np.y && !xl) kind = 3;
 	else if (np.x != np.y && mac_ok(a, np.x, np.y)) kind = 2;
 	else if (xl && yl) kind = (np.x != np.y) ? 1 : 0;
-	else if (xl || (!yl && a.center[np.x].w <= a.center[np.y].w)) kind = 4;
+	else if (xl || (!yl && trav_center(a, np.x).w <= trav_center(a, np.y).w)) kind = 4;
 	else kind = 5;
-	// bit 0: np.x is a target of this rank, bit 1: np.y is; untouched pairs (and their
-	// descendants) are dropped.  With one rank every node is a target (flags = 3).
-	flags = 0;
-	if (kind) flags = (node_mine(a, np.x) ? 1 : 0) | (node_mine(a, np.y) ? 2 : 0);
-	return flags ? kind : 0;
+	if (!kind) flags = 0;
+	return kind;
 }
 
 __device__ __forceinline__ int expand_pair(int kind, int2 np, int2 *out)
@@ -237,7 +241,7 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 template <int G>
 __global__ void __launch_bounds__(256)
 p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap, const float *__restrict__ spos,
-           float *__restrict__ acc, int64_t n, int L, float eps2)
+           float *__restrict__ acc, int64_t n, int L, float eps2, PeerTab peers)
 {
 	const int lane = threadIdx.x & (G - 1);
 	const int groups = (gridDim.x * blockDim.x) / G;
@@ -258,6 +262,13 @@ p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap
 			if (!((flags >> dir) & 1)) continue; // another rank owns these targets
 			const int64_t ti = dir ? i2 : i1, si = dir ? i1 : i2;
 			const int tm = dir ? m2 : m1, sm = dir ? m1 : m2;
+			// multi-GPU: the particles of a remote source leaf are read from their owner's published positions
+			const float *__restrict__ src = spos;
+			if (peers.g > 0)
+			{
+				const int o = (dir ? l1 : l2) >> (L - peers.g);
+				if (o != peers.me) src = peers.pos[o];
+			}
 			for (int h0 = 0; h0 < tm; h0 += G)
 			{
 				const int h = h0 + lane;
@@ -268,7 +279,7 @@ p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap
 				for (int g0 = 0; g0 < sm; g0 += G)
 				{
 					const int gl = g0 + lane;
-					const float *sp = spos + 3 * (si + (gl < sm ? gl : 0));
+					const float *sp = src + 3 * (si + (gl < sm ? gl : 0));
 					const float sx = sp[0], sy = sp[1], sz = sp[2];
 					const int ng = min(G, sm - g0);
 					for (int g = 0; g < ng; ++g)
@@ -343,6 +354,7 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 		p.ev_ok = true;
 	}
 	if (p.n == n && p.order == c.order && p.dens == c.dens_inhom && p.max_level == c.max_level) return NBCO_OK;
+	if (ctx->peer.active) { set_error("n / order / levels cannot change while peers are attached (published buffers would move)"); return NBCO_ERR_INVALID; }
 	if (n < 8) { set_error("fmm3_kd needs n >= 8 (got %lld)", (long long)n); return NBCO_ERR_INVALID; }
 	if (n >= (1ll << 31)) { set_error("n must be < 2^31"); return NBCO_ERR_INVALID; }
 	const int L = plan_levels(n, c.order, c.dens_inhom, c.max_level);
@@ -380,6 +392,13 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	return NBCO_OK;
 }
 
+int fmm3_peer_buffers(nbco_ctx *ctx, int64_t n, void **center, void **mpole)
+{
+	NBCO_TRY(ensure_plan(ctx, n));
+	*center = ctx->fmm->center.p; *mpole = ctx->fmm->mpole.p;
+	return NBCO_OK;
+}
+
 #define LAUNCHED(ctx) do { ++(ctx)->launches; } while (0)
 
 static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_pos, float *d_acc, const float *d_param, bool fuse_elastic, bool rebuild)
@@ -388,7 +407,24 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	const int64_t n = p.n;
 	const int L = p.L;
 	const nbco_config &c = ctx->cfg;
-	TreeData t{p.center.as<float4>(), p.kd.size2.as<float>(), p.mpole.as<float>(), p.local.as<float>(), p.sM, p.sL};
+	TreeData t{p.center.as<float4>(), p.kd.size2.as<float>(), p.mpole.as<float>(), p.local.as<float>(), p.sM, p.sL, {}};
+	// multi-GPU: rank r of 2^g owns the subtree of node (g, r): a contiguous range of leaves and particles
+	int g = 0;
+	while ((1 << g) < c.world) ++g;
+	PeerState &ps = ctx->peer;
+	const bool peer = ps.active && c.world > 1;
+	if (peer && ps.n != n) { set_error("peer mode was set up for n = %lld", (long long)ps.n); return NBCO_ERR_INVALID; }
+	// peer mode: only the own subtree is built and summarised here (pg = g); replicated mode: everything (pg = 0)
+	const int pg = peer ? g : 0, pr = peer ? c.rank : 0;
+	for (int q = 0; q < kMaxPeers; ++q) { t.peers.center[q] = t.center; t.peers.mpole[q] = t.mpole; t.peers.pos[q] = d_pos; }
+	t.peers.g = pg; t.peers.me = pr;
+	if (peer)
+		for (int q = 0; q < c.world; ++q)
+		{
+			t.peers.center[q] = (const float4 *)ps.center[q]; t.peers.mpole[q] = (const float *)ps.mpole[q];
+			t.peers.pos[q] = (const float *)((const char *)ps.pubp[q] + kPeerHeader);
+		}
+	const int64_t own_lo = seg_start(n, pr, pg), own_hi = seg_start(n, pr + 1, pg);
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_KDTOP], st));
 	const float *spos = d_pos; // tree-ordered positions the passes read
@@ -399,21 +435,37 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	}
 	else
 	{
-		NBCO_TRY(kd_build(ctx, p.kd, d_pos, p.ev[PH_KDBOTTOM]));
+		if (peer && !ps.have_full)
+		{
+			// every rank holds only its own range: publish it, pull the others' (the rebuild splits ALL particles)
+			NBCO_TRY(peer_publish(ctx, d_pos, 0, n)); NBCO_TRY(peer_publish(ctx, d_pos + 3*n, 1, n));
+			NBCO_TRY(peer_barrier(ctx));
+			NBCO_TRY(peer_pull(ctx, d_pos, 0, n)); NBCO_TRY(peer_pull(ctx, d_pos + 3*n, 1, n));
+			NBCO_TRY(peer_barrier(ctx)); // the mirrors are rewritten below
+		}
+		NBCO_TRY(kd_build(ctx, p.kd, d_pos, p.ev[PH_KDBOTTOM], pr, pg));
 		NBCO_CUDA(cudaEventRecord(p.ev[PH_PERMUTE], st));
 		if (c.unsort)
 			spos = p.kd.spos.as<float>();
 		else
 		{
-			// leave pos and the velocities behind it in tree order (:1359-1360,1758-1759)
-			NBCO_CUDA(cudaMemcpyAsync(d_pos, p.kd.spos.p, 12 * (size_t)n, cudaMemcpyDeviceToDevice, st));
-			gather3_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(d_pos + 3*n, p.kd.perm.as<int>(), p.tmp3.as<float>(), n); LAUNCHED(ctx);
-			NBCO_CUDA(cudaMemcpyAsync(d_pos + 3*n, p.tmp3.p, 12 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+			// leave pos and the velocities behind it in tree order (:1359-1360,1758-1759); peer mode: own range only
+			const int64_t cnt = own_hi - own_lo;
+			NBCO_CUDA(cudaMemcpyAsync(d_pos + 3*own_lo, p.kd.spos.as<float>() + 3*own_lo, 12 * (size_t)cnt, cudaMemcpyDeviceToDevice, st));
+			gather3_kernel<<<grid_for(cnt, 256, ctx->sm_count, 8), 256, 0, st>>>(d_pos + 3*n, p.kd.perm.as<int>() + own_lo, p.tmp3.as<float>() + 3*own_lo, cnt); LAUNCHED(ctx);
+			NBCO_CUDA(cudaMemcpyAsync(d_pos + 3*n + 3*own_lo, p.tmp3.as<float>() + 3*own_lo, 12 * (size_t)cnt, cudaMemcpyDeviceToDevice, st));
 		}
+		if (peer) ps.have_full = false;
 	}
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_UPWARD], st));
 	NBCO_CUDA(cudaMemsetAsync(p.local.p, 0, sizeof(float) * (size_t)p.ntot * p.sL, st));
-	ops.upward(ctx, t, spos, n, L);
+	if (peer) NBCO_TRY(peer_publish(ctx, d_pos, 0, n));
+	ops.upward(ctx, t, spos, n, L, pr, pg, 0);
+	if (peer)
+	{
+		NBCO_TRY(peer_barrier(ctx)); // every subtree is summarised and every position range published
+		ops.upward(ctx, t, spos, n, L, pr, pg, 1);
+	}
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_TRAVERSE], st));
 	TravArgs a;
@@ -422,10 +474,8 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	a.cnt = p.cnt.as<u32>();
 	a.cap_p2p = a.cap_m2l = p.cap_list; a.cap_front = p.cap_front;
 	a.n = n; a.ntot = p.ntot; a.L = L; a.m2l_first = c.m2l_first; a.radius = c.radius;
-	// multi-GPU: rank r of 2^g owns the subtree of node (g, r): a contiguous range of leaves and particles
-	int g = 0;
-	while ((1 << g) < c.world) ++g;
 	a.sh_lo = seg_start(n, c.rank, g); a.sh_hi = seg_start(n, c.rank + 1, g);
+	a.peers = t.peers;
 	traverse_init_kernel<<<1, 32, 0, st>>>(p.frontA.as<int2>(), a.cnt); LAUNCHED(ctx);
 	// breadth first: a pair is split at most once per round, 2L + 2 rounds always suffice.  (A depth-first
 	// tail with private stacks was measured 2-25x slower on B200, profiles/r01_notes.md.)
@@ -464,7 +514,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 		const int blocks = ctx->sm_count * 8;
 #define P2P_LAUNCH(G)                                                                                              \
 		do {                                                                                                       \
-			p2p_kernel<G><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2); \
+			p2p_kernel<G><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2, t.peers); \
 		} while (0)
 		if (p.mlt_max <= 4) P2P_LAUNCH(4);
 		else if (p.mlt_max <= 8) P2P_LAUNCH(8);
@@ -480,6 +530,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_L2L], st));
 	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll,
 	             p.ev[PH_L2P]);
+	if (peer) NBCO_TRY(peer_barrier(ctx)); // nobody reads this rank's centres / multipoles / positions any more
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_COUNT], st));
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;
@@ -522,6 +573,12 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 		{
 			++p.counter;
 			return NBCO_OK;
+		}
+		if (ctx->peer.active)
+		{
+			// the ranks pass the peer barriers in lockstep: an evaluation cannot be repeated by one rank alone
+			set_error("peer mode: interaction lists exceed capacity (%u p2p, %u m2l of %u)", h[0], h[1], p.cap_list);
+			return NBCO_ERR_OVERFLOW;
 		}
 		// a list or a frontier did not fit: grow and redo this evaluation.  With unsort == 0 the
 		// caller's arrays are already in tree order and the tree is valid: do not build again.

@@ -85,6 +85,26 @@ __device__ __forceinline__ void write_box(const TreeGeom &g, int node, const flo
 }
 
 
+// Multi-GPU over peer memory (peer.cu): rank r of 2^g owns the subtree of kd node (g, r).  Every rank keeps
+// full-size node arrays but fills only its own subtree (levels >= g) and the replicated top (levels < g);
+// data of a remote node or leaf is read from its owner's arrays, mapped through CUDA IPC over NVLink.
+// Single GPU / replicated mode: g = 0 and slot 0 holds the local arrays.
+constexpr int kMaxPeers = 8;
+struct PeerTab
+{
+	const float4 *center[kMaxPeers];
+	const float *mpole[kMaxPeers];
+	const float *pos[kMaxPeers];   // tree-ordered positions: every owner publishes its own range
+	int g, me;
+};
+
+__device__ __forceinline__ int node_owner(const PeerTab &p, int node)
+{
+	if (p.g == 0) return 0;
+	const int l = node_level(node);
+	return l < p.g ? p.me : ((node - kd_beg(l)) >> (l - p.g));
+}
+
 struct TreeData
 {
 	float4 *center;   // xyz = centre of charge, w = kd_size of the node's box (read by the MAC)
@@ -92,7 +112,15 @@ struct TreeData
 	float *mpole;     // sM floats per node, symmetric tuple orders 0..P-1
 	float *local;     // sL floats per node, traceless tuple orders 0..P
 	int sM, sL;
+	PeerTab peers;
 };
+
+// centre / multipole tuple of a node that may live on another GPU
+__device__ __forceinline__ float4 node_center(const TreeData &t, int node) { return t.peers.center[node_owner(t.peers, node)][node]; }
+__device__ __forceinline__ const float *node_mpole(const TreeData &t, int node)
+{
+	return t.peers.mpole[node_owner(t.peers, node)] + (int64_t)node * t.sM;
+}
 
 // kd-tree geometry and build scratch (kdtree.cu)
 struct KdTree
@@ -104,7 +132,9 @@ struct KdTree
 	bool bottom_attr = false;
 };
 int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L);
-int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom);
+// r, g: build the top g levels over all particles and, below them, only the subtree of node (g, r)
+// (g = 0: the whole tree)
+int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom, int r, int g);
 void kd_release(KdTree &t);
 
 // leaf (or node of level l) that owns sorted position j: floor(2^l j / n) (:162-164) without a 64-bit
@@ -143,7 +173,9 @@ __device__ __forceinline__ void self_p2p(float *f, const float *__restrict__ spo
 // to compile, the reference's single TU takes > 4 min).
 struct OrderOps
 {
-	void (*upward)(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L);
+	// part 0: P2M and M2M of rank r's subtree (levels L .. g); part 1: the replicated top (levels g-1 .. 0),
+	// whose level-g children are read from their owners.  One rank: g = 0, part 0 is the whole pass.
+	void (*upward)(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L, int r, int g, int part);
 	void (*m2l)(nbco_ctx *ctx, TreeData t, const int2 *list, const unsigned *count, unsigned cap, float eps2);
 	// rank r of 2^g ranks pushes locals down its own subtree (plus the ancestors of its root) only
 	void (*downward)(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,

@@ -47,10 +47,10 @@ __device__ __forceinline__ void atomic_add_tuple(float *__restrict__ dst, const 
 // leaf centres (centerLeaves_krnl, appel.cuh:226-243: sequential fp32 mean) + P2M (:231-250)
 template <int P>
 __global__ void __launch_bounds__(128)
-leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L)
+leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L, int first, int count)
 {
-	const int m = 1 << L, beg = kd_beg(L);
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+	const int beg = kd_beg(L);
+	for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < first + count; i += gridDim.x * blockDim.x)
 	{
 		int64_t st = seg_start(n, i, L);
 		int cnt = (int)(seg_start(n, i + 1, L) - st);
@@ -75,13 +75,13 @@ leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L)
 // storage order, bit-exact), the P2M sums are accumulated per lane and reduced by butterfly shuffles
 template <int P, int G>
 __global__ void __launch_bounds__(128)
-leaf_p2m_group_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L)
+leaf_p2m_group_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L, int first, int count)
 {
-	const int m = 1 << L, beg = kd_beg(L);
+	const int beg = kd_beg(L);
 	const int lane = threadIdx.x & (G - 1);
 	const int groups = (gridDim.x * blockDim.x) / G;
 	const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) / G; i < m; i += groups)
+	for (int i = first + (blockIdx.x * blockDim.x + threadIdx.x) / G; i < first + count; i += groups)
 	{
 		const int64_t st = seg_start(n, i, L);
 		const int cnt = (int)(seg_start(n, i + 1, L) - st);
@@ -128,7 +128,7 @@ __device__ __forceinline__ void m2m_node(const TreeData &t, int node, int64_t n,
 	const float m0 = (float)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
 	const float m1 = (float)(seg_start(n, 2*i + 2, l + 1) - seg_start(n, 2*i + 1, l + 1));
 	const float mt = (float)(seg_start(n, i + 1, l) - seg_start(n, i, l));
-	const float4 a = t.center[c0], b = t.center[c1];
+	const float4 a = node_center(t, c0), b = node_center(t, c1); // level-g children of the replicated top live on their owners
 	// coord = (m0*c0 + m1*c1) / m with separately rounded products (host arithmetic, :345-348)
 	float cx = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.x), __fmul_rn(m1, b.x)), mt);
 	float cy = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.y), __fmul_rn(m1, b.y)), mt);
@@ -139,9 +139,9 @@ __device__ __forceinline__ void m2m_node(const TreeData &t, int node, int64_t n,
 	if constexpr (P >= 3)
 	{
 		float Mi[pad4<sym_off(P)>()];
-		load_tuple<sym_off(P)>(Mi, t.mpole + (int64_t)c0 * t.sM);
+		load_tuple<sym_off(P)>(Mi, node_mpole(t, c0));
 		m2m_acc<P>(M, Mi, cx - a.x, cy - a.y, cz - a.z);
-		load_tuple<sym_off(P)>(Mi, t.mpole + (int64_t)c1 * t.sM);
+		load_tuple<sym_off(P)>(Mi, node_mpole(t, c1));
 		m2m_acc<P>(M, Mi, cx - b.x, cy - b.y, cz - b.z);
 	}
 	M[0] = mt;
@@ -150,20 +150,22 @@ __device__ __forceinline__ void m2m_node(const TreeData &t, int node, int64_t n,
 }
 
 template <int P>
-__global__ void __launch_bounds__(128) m2m_level_kernel(TreeData t, int64_t n, int l)
+__global__ void __launch_bounds__(128) m2m_level_kernel(TreeData t, int64_t n, int l, int first, int count)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < (1 << l)) m2m_node<P>(t, kd_beg(l) + i, n, l, i);
+	if (i < count) m2m_node<P>(t, kd_beg(l) + first + i, n, l, first + i);
 }
 
-// levels ltop .. 0 in one CTA (few nodes, dependent launches otherwise)
+// levels lhi .. llo in one CTA (few nodes, dependent launches otherwise); of a level l >= g only the nodes
+// of rank r's subtree
 template <int P>
-__global__ void __launch_bounds__(256) m2m_top_kernel(TreeData t, int64_t n, int ltop)
+__global__ void __launch_bounds__(256) m2m_top_kernel(TreeData t, int64_t n, int lhi, int llo, int r, int g)
 {
-	for (int l = ltop; l >= 0; --l)
+	for (int l = lhi; l >= llo; --l)
 	{
-		for (int i = threadIdx.x; i < (1 << l); i += blockDim.x)
-			m2m_node<P>(t, kd_beg(l) + i, n, l, i);
+		const int first = l >= g ? r << (l - g) : 0, count = l >= g ? 1 << (l - g) : 1 << l;
+		for (int i = threadIdx.x; i < count; i += blockDim.x)
+			m2m_node<P>(t, kd_beg(l) + first + i, n, l, first + i);
 		__syncthreads();
 	}
 }
@@ -181,7 +183,7 @@ m2l_kernel(TreeData t, const int2 *__restrict__ list, const u32 *__restrict__ co
 		int2 np = list[w];
 		const int flags = (np.x >> kFlagShift) & 3; // bit 0: np.x is a target of this rank, bit 1: np.y
 		np.x &= kNodeMask;
-		const float4 c1 = t.center[np.x], c2 = t.center[np.y];
+		const float4 c1 = node_center(t, np.x), c2 = node_center(t, np.y);
 		float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z;
 		const float r2 = dx*dx + dy*dy + dz*dz + eps2;
 		const float rinv = 1.f / sqrtf(r2); // IEEE sqrt and divide like the reference (:636-637); M2L is not flop-bound
@@ -190,7 +192,7 @@ m2l_kernel(TreeData t, const int2 *__restrict__ list, const u32 *__restrict__ co
 		// target np.x, source np.y
 		if (flags & 1)
 		{
-			load_tuple<sym_off(P)>(M, t.mpole + (int64_t)np.y * t.sM);
+			load_tuple<sym_off(P)>(M, node_mpole(t, np.y));
 #pragma unroll
 			for (int k = 0; k < pad4<trl_off(P + 1)>(); ++k) Lq[k] = 0.f;
 			m2l_acc<P>(Lq, M, dx, dy, dz, rinv);
@@ -199,7 +201,7 @@ m2l_kernel(TreeData t, const int2 *__restrict__ list, const u32 *__restrict__ co
 		// target np.y, source np.x
 		if (flags & 2)
 		{
-			load_tuple<sym_off(P)>(M, t.mpole + (int64_t)np.x * t.sM);
+			load_tuple<sym_off(P)>(M, node_mpole(t, np.x));
 #pragma unroll
 			for (int k = 0; k < pad4<trl_off(P + 1)>(); ++k) Lq[k] = 0.f;
 			m2l_acc<P>(Lq, M, -dx, -dy, -dz, rinv);
@@ -283,19 +285,26 @@ constexpr int kTopLevels = 7; // levels 0..7 of the upward / 2..8 of the downwar
 template <int P>
 struct OrderImpl
 {
-	static void upward(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L)
+	static void upward(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L, int r, int g, int part)
 	{
 		cudaStream_t st = ctx->stream;
-		const int mlt_max = (int)((n - 1) / (1ll << L) + 1);
-		if (mlt_max <= 8) leaf_p2m_kernel<P><<<grid_for(1ll << L, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L);
-		else if (mlt_max <= 16) leaf_p2m_group_kernel<P, 16><<<grid_for(16ll << L, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L);
-		else leaf_p2m_group_kernel<P, 32><<<grid_for(32ll << L, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L);
-		++ctx->launches;
-		for (int l = L - 1; l > kTopLevels; --l)
+		if (part == 1)
 		{
-			m2m_level_kernel<P><<<((1 << l) + 127) / 128, 128, 0, st>>>(t, n, l); ++ctx->launches;
+			if (g > 0) { m2m_top_kernel<P><<<1, 256, 0, st>>>(t, n, g - 1, 0, r, g); ++ctx->launches; }
+			return;
 		}
-		m2m_top_kernel<P><<<1, 256, 0, st>>>(t, n, std::min(L - 1, kTopLevels)); ++ctx->launches;
+		const int mlt_max = (int)((n - 1) / (1ll << L) + 1);
+		const int first = r << (L - g), count = 1 << (L - g);
+		if (mlt_max <= 8) leaf_p2m_kernel<P><<<grid_for(count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
+		else if (mlt_max <= 16) leaf_p2m_group_kernel<P, 16><<<grid_for(16ll * count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
+		else leaf_p2m_group_kernel<P, 32><<<grid_for(32ll * count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
+		++ctx->launches;
+		for (int l = L - 1; l > kTopLevels && l >= g; --l)
+		{
+			const int cnt = 1 << (l - g);
+			m2m_level_kernel<P><<<(cnt + 127) / 128, 128, 0, st>>>(t, n, l, r << (l - g), cnt); ++ctx->launches;
+		}
+		if (std::min(L - 1, kTopLevels) >= g) { m2m_top_kernel<P><<<1, 256, 0, st>>>(t, n, std::min(L - 1, kTopLevels), g, r, g); ++ctx->launches; }
 	}
 	static void m2l(nbco_ctx *ctx, TreeData t, const int2 *list, const unsigned *count, unsigned cap, float eps2)
 	{

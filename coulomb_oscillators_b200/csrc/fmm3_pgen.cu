@@ -180,10 +180,10 @@ __device__ void g_l2p_field(float *f, const float *S, int P, float dx, float dy,
 }
 
 // ---- kernels: same structure as fmm3_order.cuh ----
-__global__ void __launch_bounds__(128) g_leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L, int P)
+__global__ void __launch_bounds__(128) g_leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L, int P, int first, int count)
 {
-	const int m = 1 << L, beg = kd_beg(L), offM = g_sym_off(P);
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+	const int beg = kd_beg(L), offM = g_sym_off(P);
+	for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < first + count; i += gridDim.x * blockDim.x)
 	{
 		int64_t st = seg_start(n, i, L);
 		int cnt = (int)(seg_start(n, i + 1, L) - st);
@@ -209,7 +209,7 @@ __device__ void g_m2m_node(const TreeData &t, int node, int64_t n, int l, int i,
 	const float m0 = (float)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
 	const float m1 = (float)(seg_start(n, 2*i + 2, l + 1) - seg_start(n, 2*i + 1, l + 1));
 	const float mt = (float)(seg_start(n, i + 1, l) - seg_start(n, i, l));
-	const float4 a = t.center[c0], b = t.center[c1];
+	const float4 a = node_center(t, c0), b = node_center(t, c1);
 	float cx = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.x), __fmul_rn(m1, b.x)), mt);
 	float cy = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.y), __fmul_rn(m1, b.y)), mt);
 	float cz = __fdiv_rn(__fadd_rn(__fmul_rn(m0, a.z), __fmul_rn(m1, b.z)), mt);
@@ -217,8 +217,8 @@ __device__ void g_m2m_node(const TreeData &t, int node, int64_t n, int l, int i,
 	for (int k = 0; k < offM; ++k) M[k] = 0.f;
 	if (P >= 3)
 	{
-		g_m2m_acc(M, t.mpole + (int64_t)c0 * t.sM, P, cx - a.x, cy - a.y, cz - a.z);
-		g_m2m_acc(M, t.mpole + (int64_t)c1 * t.sM, P, cx - b.x, cy - b.y, cz - b.z);
+		g_m2m_acc(M, node_mpole(t, c0), P, cx - a.x, cy - a.y, cz - a.z);
+		g_m2m_acc(M, node_mpole(t, c1), P, cx - b.x, cy - b.y, cz - b.z);
 	}
 	M[0] = mt;
 	float *out = t.mpole + (int64_t)node * t.sM;
@@ -226,18 +226,19 @@ __device__ void g_m2m_node(const TreeData &t, int node, int64_t n, int l, int i,
 	t.center[node] = make_float4(cx, cy, cz, t.size2[node]);
 }
 
-__global__ void __launch_bounds__(128) g_m2m_level_kernel(TreeData t, int64_t n, int l, int P)
+__global__ void __launch_bounds__(128) g_m2m_level_kernel(TreeData t, int64_t n, int l, int P, int first, int count)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < (1 << l)) g_m2m_node(t, kd_beg(l) + i, n, l, i, P);
+	if (i < count) g_m2m_node(t, kd_beg(l) + first + i, n, l, first + i, P);
 }
 
-__global__ void __launch_bounds__(256) g_m2m_top_kernel(TreeData t, int64_t n, int ltop, int P)
+__global__ void __launch_bounds__(256) g_m2m_top_kernel(TreeData t, int64_t n, int lhi, int llo, int P, int r, int g)
 {
-	for (int l = ltop; l >= 0; --l)
+	for (int l = lhi; l >= llo; --l)
 	{
-		for (int i = threadIdx.x; i < (1 << l); i += blockDim.x)
-			g_m2m_node(t, kd_beg(l) + i, n, l, i, P);
+		const int first = l >= g ? r << (l - g) : 0, count = l >= g ? 1 << (l - g) : 1 << l;
+		for (int i = threadIdx.x; i < count; i += blockDim.x)
+			g_m2m_node(t, kd_beg(l) + first + i, n, l, first + i, P);
 		__syncthreads();
 	}
 }
@@ -252,7 +253,7 @@ g_m2l_kernel(TreeData t, const int2 *__restrict__ list, const unsigned *__restri
 		int2 np = list[w];
 		const int flags = (np.x >> kFlagShift) & 3;
 		np.x &= kNodeMask;
-		const float4 c1 = t.center[np.x], c2 = t.center[np.y];
+		const float4 c1 = node_center(t, np.x), c2 = node_center(t, np.y);
 		float dx = c1.x - c2.x, dy = c1.y - c2.y, dz = c1.z - c2.z;
 		const float rinv = 1.f / sqrtf(dx*dx + dy*dy + dz*dz + eps2);
 		dx *= rinv; dy *= rinv; dz *= rinv;
@@ -263,7 +264,7 @@ g_m2l_kernel(TreeData t, const int2 *__restrict__ list, const unsigned *__restri
 			const int tgt = dir ? np.y : np.x, src = dir ? np.x : np.y;
 			const float s = dir ? -1.f : 1.f;
 			for (int k = 0; k < offL; ++k) Lq[k] = 0.f;
-			g_m2l_acc(Lq, t.mpole + (int64_t)src * t.sM, P, s * dx, s * dy, s * dz, rinv);
+			g_m2l_acc(Lq, node_mpole(t, src), P, s * dx, s * dy, s * dz, rinv);
 			float *dst = t.local + (int64_t)tgt * t.sL;
 			for (int k = 1; k < offL; ++k) atomicAdd(dst + k, Lq[k]);
 		}
@@ -330,15 +331,22 @@ constexpr int kTopLevels = 7;
 template <int P>
 struct GenImpl
 {
-	static void upward(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L)
+	static void upward(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L, int r, int g, int part)
 	{
 		cudaStream_t st = ctx->stream;
-		g_leaf_p2m_kernel<<<grid_for(1ll << L, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, P); ++ctx->launches;
-		for (int l = L - 1; l > kTopLevels; --l)
+		if (part == 1)
 		{
-			g_m2m_level_kernel<<<((1 << l) + 127) / 128, 128, 0, st>>>(t, n, l, P); ++ctx->launches;
+			if (g > 0) { g_m2m_top_kernel<<<1, 256, 0, st>>>(t, n, g - 1, 0, P, r, g); ++ctx->launches; }
+			return;
 		}
-		g_m2m_top_kernel<<<1, 256, 0, st>>>(t, n, std::min(L - 1, kTopLevels), P); ++ctx->launches;
+		const int first = r << (L - g), count = 1 << (L - g);
+		g_leaf_p2m_kernel<<<grid_for(count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, P, first, count); ++ctx->launches;
+		for (int l = L - 1; l > kTopLevels && l >= g; --l)
+		{
+			const int cnt = 1 << (l - g);
+			g_m2m_level_kernel<<<(cnt + 127) / 128, 128, 0, st>>>(t, n, l, P, r << (l - g), cnt); ++ctx->launches;
+		}
+		if (std::min(L - 1, kTopLevels) >= g) { g_m2m_top_kernel<<<1, 256, 0, st>>>(t, n, std::min(L - 1, kTopLevels), g, P, r, g); ++ctx->launches; }
 	}
 	static void m2l(nbco_ctx *ctx, TreeData t, const int2 *list, const unsigned *count, unsigned cap, float eps2)
 	{

@@ -83,10 +83,10 @@ __global__ void root_box_kernel(TreeGeom g, const u32 *__restrict__ bb)
 // =====================================================================================
 struct TileRange { int64_t a, b, s0; int seg; };
 
-__device__ __forceinline__ TileRange tile_range(int64_t n, int l, int tps)
+__device__ __forceinline__ TileRange tile_range(int64_t n, int l, int tps, int seg0)
 {
 	TileRange r;
-	r.seg = blockIdx.x / tps;
+	r.seg = seg0 + blockIdx.x / tps;
 	int t = blockIdx.x % tps;
 	r.s0 = seg_start(n, r.seg, l);
 	int64_t s1 = seg_start(n, r.seg + 1, l);
@@ -133,12 +133,12 @@ __global__ void __launch_bounds__(256) to_soa_kernel(const float *__restrict__ p
 // keys of level l (evalKeys_kdtree, :158-192) + histogram of key bits 31..21
 __global__ void __launch_bounds__(kSelThreads)
 keygen_hist_kernel(const float *__restrict__ soa, const int *__restrict__ splitdim, const u32 *__restrict__ idx,
-                   u32 *__restrict__ keys, u32 *__restrict__ hist, int64_t n, int l, int tps)
+                   u32 *__restrict__ keys, u32 *__restrict__ hist, int64_t n, int l, int tps, int seg0)
 {
 	__shared__ u32 sh[kBins0];
 	for (int b = threadIdx.x; b < kBins0; b += kSelThreads) sh[b] = 0;
 	__syncthreads();
-	const TileRange r = tile_range(n, l, tps);
+	const TileRange r = tile_range(n, l, tps, seg0);
 	const int axis = splitdim[kd_beg(l) + r.seg];
 	for (int64_t j0 = r.a; j0 < r.b; j0 += kSelThreads)
 	{
@@ -160,13 +160,13 @@ keygen_hist_kernel(const float *__restrict__ soa, const int *__restrict__ splitd
 // histogram of the next digit over the keys that share the prefix selected so far
 template <int PASS>
 __global__ void __launch_bounds__(kSelThreads)
-sel_hist_kernel(const u32 *__restrict__ keys, const SegSel *__restrict__ sel, u32 *__restrict__ hist, int64_t n, int l, int tps)
+sel_hist_kernel(const u32 *__restrict__ keys, const SegSel *__restrict__ sel, u32 *__restrict__ hist, int64_t n, int l, int tps, int seg0)
 {
 	constexpr int kHi = PASS == 1 ? 21 : 10, kLo = PASS == 1 ? 10 : 0, kBins = PASS == 1 ? 2048 : 1024;
 	__shared__ u32 sh[kBins];
 	for (int b = threadIdx.x; b < kBins; b += kSelThreads) sh[b] = 0;
 	__syncthreads();
-	const TileRange r = tile_range(n, l, tps);
+	const TileRange r = tile_range(n, l, tps, seg0);
 	const u32 want = sel[r.seg].prefix >> kHi;
 	for (int64_t j0 = r.a; j0 < r.b; j0 += kSelThreads)
 	{
@@ -182,12 +182,12 @@ sel_hist_kernel(const u32 *__restrict__ keys, const SegSel *__restrict__ sel, u3
 // one block per segment: find the bin that holds rank krem, descend into it, clear the histogram
 template <int PASS>
 __global__ void __launch_bounds__(256)
-sel_pick_kernel(SegSel *__restrict__ sel, SegCur *__restrict__ cur, u32 *__restrict__ hist, int64_t n, int l)
+sel_pick_kernel(SegSel *__restrict__ sel, SegCur *__restrict__ cur, u32 *__restrict__ hist, int64_t n, int l, int seg0)
 {
 	constexpr int kLo = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0), kBins = PASS == 2 ? 1024 : 2048, kPer = kBins / 256;
 	__shared__ u32 wsum[8];
 	__shared__ u32 s_found[3];
-	const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const int seg = seg0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	u32 *h = hist + (int64_t)seg * kBins0;
 	SegSel st;
 	if (PASS == 0)
@@ -237,11 +237,11 @@ sel_pick_kernel(SegSel *__restrict__ sel, SegCur *__restrict__ cur, u32 *__restr
 // unordered two-way partition of the ids of every segment around its pivot key
 __global__ void __launch_bounds__(kSelThreads)
 partition_kernel(const u32 *__restrict__ keys, const u32 *__restrict__ idx_in, u32 *__restrict__ idx_out, u32 *__restrict__ tie,
-                 const SegSel *__restrict__ sel, SegCur *__restrict__ cur, int64_t n, int l, int tps)
+                 const SegSel *__restrict__ sel, SegCur *__restrict__ cur, int64_t n, int l, int tps, int seg0)
 {
 	__shared__ u32 wcnt[8][3];
 	__shared__ u32 base[3];
-	const TileRange r = tile_range(n, l, tps);
+	const TileRange r = tile_range(n, l, tps, seg0);
 	if (r.a >= r.b) return;
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	const u32 lt_mask = (1u << lane) - 1u;
@@ -312,9 +312,9 @@ __device__ __forceinline__ bool tie_less(const float *__restrict__ pos, u32 a, u
 // segments whose pivot key is shared by particles on both sides: rank the tied ids
 __global__ void __launch_bounds__(256)
 ties_kernel(const float *__restrict__ pos, const int *__restrict__ chain, const u32 *__restrict__ tie, u32 *__restrict__ idx_out,
-            const SegSel *__restrict__ sel, SegCur *__restrict__ cur, int64_t n, int l)
+            const SegSel *__restrict__ sel, SegCur *__restrict__ cur, int64_t n, int l, int seg0)
 {
-	const int seg = blockIdx.x;
+	const int seg = seg0 + blockIdx.x;
 	const SegSel st = sel[seg];
 	const u32 need = st.krem + 1;
 	if (st.eq == need) return;
@@ -335,10 +335,11 @@ ties_kernel(const float *__restrict__ pos, const int *__restrict__ chain, const 
 
 // boxes of level l+1 from the pivots of level l (evalBox_krnl, :109-137)
 __global__ void __launch_bounds__(256)
-evalbox_top_kernel(TreeGeom g, const SegSel *__restrict__ sel, const SegCur *__restrict__ cur, int l)
+evalbox_top_kernel(TreeGeom g, const SegSel *__restrict__ sel, const SegCur *__restrict__ cur, int l, int seg0, int nseg)
 {
-	const int seg = blockIdx.x * blockDim.x + threadIdx.x;
-	if (seg >= (1 << l)) return;
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= nseg) return;
+	const int seg = seg0 + k;
 	const int node = kd_beg(l) + seg, axis = g.splitdim[node], pch = g.chain[node];
 	float lb[3], rb[3];
 	for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
@@ -464,7 +465,7 @@ __device__ __forceinline__ void warp_sort_blocks(u64 (&v)[8], int lane, int B, c
 
 __global__ void __launch_bounds__(kBottomThreads, 1)
 kd_bottom_kernel(TreeGeom g, const float *__restrict__ pos, const u32 *__restrict__ idx_in,
-                 float *__restrict__ spos, int *__restrict__ perm, int64_t n, int lt, int L, int P2)
+                 float *__restrict__ spos, int *__restrict__ perm, int64_t n, int lt, int L, int P2, int blk0)
 {
 	extern __shared__ unsigned char smem_raw[];
 	BottomSmem s;
@@ -476,7 +477,7 @@ kd_bottom_kernel(TreeGeom g, const float *__restrict__ pos, const u32 *__restric
 	s.sel = reinterpret_cast<SegSel *>(s.hist + 16 * 256);
 	s.cur = reinterpret_cast<u32 *>(s.sel + 16);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int b = blockIdx.x;
+	const int b = blk0 + blockIdx.x;
 	const int64_t s0 = seg_start(n, b, lt);
 	const int c0 = (int)(seg_start(n, b + 1, lt) - s0);
 	constexpr int kPer = kBottomCap / kBottomThreads;
@@ -805,16 +806,16 @@ void kd_release(KdTree &t)
 	for (DevBuf *b : all) b->release();
 }
 
-int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom)
+int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom, int r, int g)
 {
 	cudaStream_t st = ctx->stream;
 	const int64_t n = t.n;
-	TreeGeom g{t.lbound.as<float>(), t.rbound.as<float>(), t.size2.as<float>(), t.splitdim.as<int>(), t.chain.as<int>()};
+	TreeGeom tg{t.lbound.as<float>(), t.rbound.as<float>(), t.size2.as<float>(), t.splitdim.as<int>(), t.chain.as<int>()};
 	u32 *bb = t.bbox.as<u32>();
 	static const u32 bb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
 	NBCO_CUDA(cudaMemcpyAsync(bb, bb_init, sizeof(bb_init), cudaMemcpyHostToDevice, st));
 	bbox_kernel<<<grid_for(n, 256, ctx->sm_count, 4), 256, 0, st>>>(pos, n, bb);
-	root_box_kernel<<<1, 32, 0, st>>>(g, bb);
+	root_box_kernel<<<1, 32, 0, st>>>(tg, bb);
 	ctx->launches += 2;
 
 	u32 *keys = t.keys.as<u32>(), *tie = t.tie.as<u32>(), *hist = t.hist.as<u32>();
@@ -832,20 +833,21 @@ int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom)
 	const u32 *iin = nullptr; // level 0 reads the identity
 	for (int l = 0; l < ltop; ++l)
 	{
-		const int nseg = 1 << l;
+		// below level g only the segments of rank r's subtree (multi-GPU: the other subtrees are built by their owners)
+		const int nseg = l >= g ? 1 << (l - g) : 1 << l, seg0 = l >= g ? r << (l - g) : 0;
 		const int64_t maxseg = ((n - 1) >> l) + 1;
 		const int tps = (int)((maxseg + kSelTile - 1) / kSelTile);
 		const int tiles = nseg * tps;
 		u32 *iout = ibuf[l & 1];
-		keygen_hist_kernel<<<tiles, kSelThreads, 0, st>>>(soa, g.splitdim, iin, keys, hist, n, l, tps);
-		sel_pick_kernel<0><<<nseg, 256, 0, st>>>(sel, cur, hist, n, l);
-		sel_hist_kernel<1><<<tiles, kSelThreads, 0, st>>>(keys, sel, hist, n, l, tps);
-		sel_pick_kernel<1><<<nseg, 256, 0, st>>>(sel, cur, hist, n, l);
-		sel_hist_kernel<2><<<tiles, kSelThreads, 0, st>>>(keys, sel, hist, n, l, tps);
-		sel_pick_kernel<2><<<nseg, 256, 0, st>>>(sel, cur, hist, n, l);
-		partition_kernel<<<tiles, kSelThreads, 0, st>>>(keys, iin, iout, tie, sel, cur, n, l, tps);
-		ties_kernel<<<nseg, 256, 0, st>>>(pos, g.chain, tie, iout, sel, cur, n, l);
-		evalbox_top_kernel<<<(nseg + 255) / 256, 256, 0, st>>>(g, sel, cur, l);
+		keygen_hist_kernel<<<tiles, kSelThreads, 0, st>>>(soa, tg.splitdim, iin, keys, hist, n, l, tps, seg0);
+		sel_pick_kernel<0><<<nseg, 256, 0, st>>>(sel, cur, hist, n, l, seg0);
+		sel_hist_kernel<1><<<tiles, kSelThreads, 0, st>>>(keys, sel, hist, n, l, tps, seg0);
+		sel_pick_kernel<1><<<nseg, 256, 0, st>>>(sel, cur, hist, n, l, seg0);
+		sel_hist_kernel<2><<<tiles, kSelThreads, 0, st>>>(keys, sel, hist, n, l, tps, seg0);
+		sel_pick_kernel<2><<<nseg, 256, 0, st>>>(sel, cur, hist, n, l, seg0);
+		partition_kernel<<<tiles, kSelThreads, 0, st>>>(keys, iin, iout, tie, sel, cur, n, l, tps, seg0);
+		ties_kernel<<<nseg, 256, 0, st>>>(pos, tg.chain, tie, iout, sel, cur, n, l, seg0);
+		evalbox_top_kernel<<<(nseg + 255) / 256, 256, 0, st>>>(tg, sel, cur, l, seg0, nseg);
 		ctx->launches += 9;
 		iin = iout;
 	}
@@ -859,8 +861,9 @@ int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom)
 	int P2 = 2; while (P2 < maxseg) P2 <<= 1;
 	while ((P2 >> (t.L - 1 - ltop)) < 2) P2 <<= 1; // the last level sorts blocks of at least 2 words
 	if (P2 > kBottomCap) { set_error("internal: bottom block %d", P2); return NBCO_ERR_INVALID; }
-	kd_bottom_kernel<<<1 << ltop, kBottomThreads, kBottomSmemBytes, st>>>(g, pos, iin, t.spos.as<float>(), t.perm.as<int>(),
-	                                                                      n, ltop, t.L, P2);
+	if (g > ltop) { set_error("more ranks than shared-memory kd blocks (2^%d > 2^%d)", g, ltop); return NBCO_ERR_INVALID; }
+	kd_bottom_kernel<<<1 << (ltop - g), kBottomThreads, kBottomSmemBytes, st>>>(tg, pos, iin, t.spos.as<float>(), t.perm.as<int>(),
+	                                                                            n, ltop, t.L, P2, r << (ltop - g));
 	++ctx->launches;
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;

@@ -101,3 +101,31 @@ def fmm_leapfrog_sharded(ctx, buf, n, d_param, dt, nsteps, group=None, gather_fi
     if gather_final:   # leave the full state on every rank (callers that only read their own range skip this)
         gather(vel, b, e)
         gather(acc, b, e)
+
+
+def peer_setup(ctx, n, group=None):
+    """Map every rank's published buffers into every other rank (csrc/peer.cu): the 192-byte CUDA IPC handle
+    blocks travel through torch.distributed (an all-gather of uint8 tensors over NCCL); afterwards the C library
+    talks to its peers directly over NVLink."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    assert ctx.cfg.rank == rank and ctx.cfg.world == world and ctx.cfg.unsort == 0
+    mine = torch.from_numpy(ctx.peer_export(n)).cuda()
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine, group=group)
+    for q, h in enumerate(every):
+        if q != rank:
+            ctx.peer_attach(q, h.cpu().numpy())
+    ctx.peer_commit()
+    dist.barrier(group=group)
+    ctx.peer_barrier()
+
+
+def fmm_leapfrog_peer(ctx, buf, n, d_param, dt, nsteps, gather_final=True):
+    """Leapfrog steps of coulombOscillatorFMMKD3 over the ranks of a peer_setup() context: ONE C call per
+    rank (nbco_integrate), all exchanges inside the kernels / the flag barrier of csrc/peer.cu."""
+    from ._lib import LEAPFROG, EVAL_COULOMB_FMM3_KD
+    ctx.integrate(LEAPFROG, EVAL_COULOMB_FMM3_KD, buf.data_ptr(), n, d_param, dt, nsteps)
+    if gather_final:
+        ctx.peer_gather(buf.data_ptr(), n)

@@ -243,6 +243,25 @@ int nbco_state_write2(const char *path, const double *h_pos_vel, int64_t n);
  * ceil(n*r/w) (fmm_cart3_kdtree.cuh:117-118). */
 void nbco_shard_range(int64_t n, int32_t rank, int32_t world, int64_t *begin, int64_t *end);
 
+/* ---- multi-GPU over NVLink peer memory (one process per GPU; csrc/peer.cu) ----
+ * Rank r of w = 2^g (cfg.rank / cfg.world, unsort = 0) owns the subtree of kd node (g, r), i.e. the tree-order
+ * range nbco_shard_range(n, r, w) of particles.  Every rank publishes its node centres, multipoles and its range of
+ * positions through CUDA IPC; the evaluator reads remote nodes / leaves straight from their owners and the ranks
+ * meet at a flag barrier in peer memory (no host round trip).  Protocol, on every rank:
+ *   nbco_peer_export(ctx, n, handles)            192 bytes = 3 cudaIpcMemHandle_t, to be sent to every other rank
+ *   nbco_peer_attach(ctx, q, handles_of_q)       for every q != rank
+ *   nbco_peer_commit(ctx)
+ * From then on nbco_force_fmm3_kd / nbco_coulomb_fmm3_kd / nbco_compute_force / nbco_integrate (leapfrog) must be
+ * called by all ranks together with the same n.  The FIRST evaluation expects the full, identical [pos | vel] on
+ * every rank; afterwards every rank holds (and steps) only its own range, and tree rebuilds fetch the other
+ * ranges from their owners.  nbco_peer_gather leaves the full [pos | vel | acc] on every rank again. */
+int nbco_peer_export(nbco_ctx *ctx, int64_t n, void *h_handles192);
+int nbco_peer_attach(nbco_ctx *ctx, int32_t peer_rank, const void *h_handles192);
+int nbco_peer_commit(nbco_ctx *ctx);
+int nbco_peer_barrier(nbco_ctx *ctx);   /* barrier + host synchronisation; NBCO_ERR_CUDA if a rank did not arrive */
+int nbco_peer_gather(nbco_ctx *ctx, void *d_buf, int64_t n);
+int nbco_peer_detach(nbco_ctx *ctx);
+
 /* ---- initial conditions and state files (host side, byte-compatible with main3.cu) ---- */
 /* initGA with the reference's fixed seed (main3.cu:114-137,662-664): h_pos_vel = 6n floats */
 int nbco_init_ga(float *h_pos_vel, int64_t n, const float *sigma_x3, const float *sigma_u3);
