@@ -156,6 +156,21 @@ __global__ void __launch_bounds__(128) m2m_level_kernel(TreeData t, int64_t n, i
 	if (i < count) m2m_node<P>(t, kd_beg(l) + first + i, n, l, first + i);
 }
 
+// levels lhi .. llo (lhi >= llo) of the subtree under node (llo, first + blockIdx.x), one CTA per subtree: the
+// upward pass is a chain of dependent levels and, launched level by level, is bound by launch latency
+template <int P>
+__global__ void __launch_bounds__(128) m2m_sub_kernel(TreeData t, int64_t n, int lhi, int llo, int first)
+{
+	const int root = first + blockIdx.x;
+	for (int l = lhi; l >= llo; --l)
+	{
+		const int cnt = 1 << (l - llo), f = root << (l - llo);
+		for (int i = threadIdx.x; i < cnt; i += blockDim.x)
+			m2m_node<P>(t, kd_beg(l) + f + i, n, l, f + i);
+		__syncthreads();
+	}
+}
+
 // levels lhi .. llo in one CTA (few nodes, dependent launches otherwise); of a level l >= g only the nodes
 // of rank r's subtree
 template <int P>
@@ -236,6 +251,20 @@ __global__ void __launch_bounds__(128) l2l_level_kernel(TreeData t, int lchild, 
 	if (i < count) l2l_node<P>(t, kd_beg(lchild) + first + i);
 }
 
+// child levels lfirst .. llast of the subtree under node (lfirst - 1, first + blockIdx.x), one CTA per subtree
+template <int P>
+__global__ void __launch_bounds__(128) l2l_sub_kernel(TreeData t, int lfirst, int llast, int first)
+{
+	const int root = first + blockIdx.x, lroot = lfirst - 1;
+	for (int l = lfirst; l <= llast; ++l)
+	{
+		const int cnt = 1 << (l - lroot), f = root << (l - lroot);
+		for (int i = threadIdx.x; i < cnt; i += blockDim.x)
+			l2l_node<P>(t, kd_beg(l) + f + i);
+		__syncthreads();
+	}
+}
+
 template <int P>
 __global__ void __launch_bounds__(256) l2l_top_kernel(TreeData t, int lfirst, int llast)
 {
@@ -281,6 +310,7 @@ l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__
 
 
 constexpr int kTopLevels = 7; // levels 0..7 of the upward / 2..8 of the downward pass run in one CTA
+constexpr int kSubLevels = 7; // deeper levels: chunks of 7 levels, one CTA per subtree (128 nodes at its widest level)
 
 template <int P>
 struct OrderImpl
@@ -299,10 +329,12 @@ struct OrderImpl
 		else if (mlt_max <= 16) leaf_p2m_group_kernel<P, 16><<<grid_for(16ll * count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
 		else leaf_p2m_group_kernel<P, 32><<<grid_for(32ll * count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
 		++ctx->launches;
-		for (int l = L - 1; l > kTopLevels && l >= g; --l)
+		// levels L-1 .. max(kTopLevels + 1, g) in chunks of kSubLevels levels, one CTA per subtree of a chunk
+		const int lstop = std::max(kTopLevels + 1, g);
+		for (int lhi = L - 1; lhi >= lstop; lhi -= kSubLevels)
 		{
-			const int cnt = 1 << (l - g);
-			m2m_level_kernel<P><<<(cnt + 127) / 128, 128, 0, st>>>(t, n, l, r << (l - g), cnt); ++ctx->launches;
+			const int llo = std::max(lhi - kSubLevels + 1, lstop);
+			m2m_sub_kernel<P><<<1 << (llo - g), 128, 0, st>>>(t, n, lhi, llo, r << (llo - g)); ++ctx->launches;
 		}
 		if (std::min(L - 1, kTopLevels) >= g) { m2m_top_kernel<P><<<1, 256, 0, st>>>(t, n, std::min(L - 1, kTopLevels), g, r, g); ++ctx->launches; }
 	}
@@ -318,10 +350,12 @@ struct OrderImpl
 		if (L >= 2)
 		{
 			l2l_top_kernel<P><<<1, 256, 0, st>>>(t, 2, std::min(L, kTopLevels + 1)); ++ctx->launches;
-			for (int l = kTopLevels + 2; l <= L; ++l)
+			// child levels kTopLevels + 2 .. L in chunks of kSubLevels, one CTA per subtree of the rank's own part
+			for (int lf = kTopLevels + 2; lf <= L; lf += kSubLevels)
 			{
-				const int first = l >= g ? r << (l - g) : r >> (g - l), count = l >= g ? 1 << (l - g) : 1;
-				l2l_level_kernel<P><<<(count + 127) / 128, 128, 0, st>>>(t, l, first, count); ++ctx->launches;
+				const int ll = std::min(lf + kSubLevels - 1, L), lroot = lf - 1;
+				const int first = lroot >= g ? r << (lroot - g) : r >> (g - lroot), count = lroot >= g ? 1 << (lroot - g) : 1;
+				l2l_sub_kernel<P><<<count, 128, 0, st>>>(t, lf, ll, first); ++ctx->launches;
 			}
 		}
 		if (ev_l2p) cudaEventRecord(ev_l2p, st);
