@@ -140,10 +140,11 @@ def run_ours(args):
     n, order = args.n, args.order
     peaks, peak_kind = measured_peaks()
 
-    # Multi-GPU (N > 1): ONE system of n particles, strong scaling.  The kd-tree is replicated, rank r of
-    # 2^g computes the subtree of node (g, r): its P2P / M2L / L2L / L2P and kick/drift; one NCCL
-    # all-gather of the drifted positions per step (parallel.fmm_leapfrog_sharded).
-    from coulomb_oscillators_b200.parallel import fmm_leapfrog_sharded
+    # Multi-GPU (N > 1): ONE system of n particles, strong scaling.  Rank r of 2^g owns the subtree of kd node
+    # (g, r): it builds, summarises, traverses and steps its own tree-order range; remote nodes and leaves are
+    # read from their owners over NVLink peer memory inside the kernels, the ranks meet at a flag barrier in
+    # peer memory (csrc/peer.cu).  NCCL only carries the IPC handles and the timing reduce.
+    from coulomb_oscillators_b200.parallel import fmm_leapfrog_peer, peer_setup
     state = nb.init_ga(n)
     par = nb.default_param(n)
     ctx = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first, rank=rank, world=world)
@@ -160,11 +161,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world > 1:
+        peer_setup(ctx, n)
+
     def run_steps(k):
         if world == 1:
             ctx.integrate(nb.LEAPFROG, ev, buf.data_ptr(), n, dpar.data_ptr(), dt, k)
         else:
-            fmm_leapfrog_sharded(ctx, buf, n, dpar.data_ptr(), dt, k)
+            fmm_leapfrog_peer(ctx, buf, n, dpar.data_ptr(), dt, k, gather_final=False)
 
     ctx.compute_force(ev, buf.data_ptr(), n, dpar.data_ptr())       # main3.cu:835-839
     run_steps(args.warmup)
@@ -198,27 +202,22 @@ def run_ours(args):
     hbuf = torch.empty(9 * n, dtype=torch.float32).pin_memory()
     hbuf.copy_(buf.cpu())
     hnp = hbuf.numpy()
-    ctx_e = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first, rank=rank, world=world)
+    ctx_e = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first) if world == 1 else ctx
     e2e_steps = max(3, min(args.steps, 8))
+    lo, hi = nb.shard_range(n, rank, world)
 
     def e2e_step():
         if world == 1:
             ctx_e.step_host(nb.LEAPFROG, ev, hnp, n, par, dt, 1)
         else:
-            # every rank uploads all positions (the tree is replicated) and its own range of vel / acc,
-            # the ranks step together, every rank reads back its own range of pos / vel / acc
-            lo, hi = nb.shard_range(n, rank, world)
-            buf[:3 * n].copy_(hbuf[:3 * n], non_blocking=True)
-            for k in (1, 2):
+            # every rank owns a tree-order range: it uploads its range of pos / vel / acc, the ranks step together
+            # (remote data moves between the GPUs inside the evaluator), every rank reads its range back
+            for k in (0, 1, 2):
                 buf[3 * n * k + 3 * lo:3 * n * k + 3 * hi].copy_(hbuf[3 * n * k + 3 * lo:3 * n * k + 3 * hi], non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            fmm_leapfrog_sharded(ctx_e, buf, n, dpar.data_ptr(), dt, 1, gather_final=False)
+            fmm_leapfrog_peer(ctx_e, buf, n, dpar.data_ptr(), dt, 1, gather_final=False)
             for k in (0, 1, 2):
                 hbuf[3 * n * k + 3 * lo:3 * n * k + 3 * hi].copy_(buf[3 * n * k + 3 * lo:3 * n * k + 3 * hi], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            # positions of the other ranks reach the host through their own read-back; here the host copy of
-            # the full position array is refreshed from the device copy the all-gather already left behind
-            hbuf[:3 * n].copy_(buf[:3 * n], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
     e2e_step()   # warm-up (allocations, first rebuild)
@@ -240,6 +239,8 @@ def run_ours(args):
     # secondary metric (BASELINE config 4): 2D fp64 FMM under PEFRL, one GPU
     fmm2d = bench_fmm2d(nb, torch, local) if (args.fmm2d and world == 1) else None
 
+    if world > 1:
+        ctx.peer_detach()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -247,7 +248,9 @@ def run_ours(args):
 
     value = n * args.steps / (ms * 1e-3)   # one system of n particles, whatever the number of GPUs
     # ---- per-phase times (CUDA events on the context stream, summed over the timed region) ----
-    bytes_eval = fmm_bytes_per_eval(n, order, info.levels, info.p2p_pairs, info.m2l_pairs)
+    bytes_eval = fmm_bytes_per_eval(n, order, info.levels, info.p2p_pairs * world, info.m2l_pairs * world)
+    if world > 1:   # per-rank share of the algorithmic bytes (rank 0's phase times are reported)
+        bytes_eval = {k: v / world for k, v in bytes_eval.items()}
     phases = {}
     total_ms = max(sum(totals.values()), 1e-9)
     for k, tot in totals.items():
@@ -263,16 +266,16 @@ def run_ours(args):
     dom_ms = totals[dom] / max(dcalls, 1)
     achieved = bytes_eval[dom] / (dom_ms * 1e-3) / 1e9
     tr = NCU_TRAFFIC.get(dom)
-    step_bytes = sum(v for k, v in bytes_eval.items() if k not in REBUILD_PHASES) \
-        + sum(bytes_eval[k] for k in REBUILD_PHASES) / 8 + 60 * n
+    step_bytes = world * (sum(v for k, v in bytes_eval.items() if k not in REBUILD_PHASES)
+                          + sum(bytes_eval[k] for k in REBUILD_PHASES) / 8) + 60 * n
     roofline = {"bound": "hbm", "kernel": SINGLE_KERNEL_PHASES[dom], "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
                 "traffic": tr["bytes"] if tr and tr["n"] == n else None, "peak_kind": peak_kind,
                 "avg_launch_ms": round(dom_ms, 4), "launches": int(dcalls),
-                "algorithmic_bytes_per_launch": int(bytes_eval[dom]),
+                "algorithmic_bytes_per_launch": int(bytes_eval[dom]),  # per rank
                 "share_of_step": round(totals[dom] / total_ms, 4),
                 "step_bytes_per_particle": round(step_bytes / n, 1),
-                "step_hbm_frac": round(step_bytes * (args.steps / (ms * 1e-3)) / 1e9 / peaks["hbm_gbs"], 4)}
+                "step_hbm_frac": round(step_bytes * (args.steps / (ms * 1e-3)) / 1e9 / (world * peaks["hbm_gbs"]), 4)}
 
     cpu = cpu_baseline(n, order, args.m2l_first, bounded=True) if world == 1 else None
     out = {
@@ -280,16 +283,15 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"3D kd-tree FMM leapfrog, N={n}, p={order}, r=1, tree_steps=8, reference initGA ICs"
-                               + (f", sharded over {world} GPUs (replicated tree, per-rank subtree evaluation, "
-                                  f"all-gather of positions per step)" if world > 1 else ""),
+                               + (f", sharded over {world} GPUs (rank r owns the subtree of kd node (log2 N, r); remote nodes / "
+                                  f"leaves read over NVLink peer memory inside the kernels, flag barriers in peer memory)" if world > 1 else ""),
                    "n": n, "order": order, "levels": int(info.levels), "p2p_pairs": int(info.p2p_pairs),
                    "m2l_pairs": int(info.m2l_pairs), "m2l_first": args.m2l_first,
                    "l2_hygiene": "inputs larger than L2 (state 36 B x N + tree slab)" if 36 * n > 126e6 else "working set may fit L2",
                    "e2e_copies": "every step: H2D [pos|vel|acc] from pinned memory + D2H of the same"},
         "roofline": roofline, "phases": phases, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s",
-                "h2d_bytes_per_step": 36 * n if world == 1 else world * 12 * n + 24 * n,
-                "d2h_bytes_per_step": 36 * n if world == 1 else world * 12 * n + 24 * n, "steps": e2e_steps},
+                "h2d_bytes_per_step": 36 * n, "d2h_bytes_per_step": 36 * n, "steps": e2e_steps},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if direct is not None:

@@ -46,7 +46,7 @@ SYMBOLS = [
     "nbco_compute_force2", "nbco_integrate2", "nbco_mean_rel_err2", "nbco_energy2", "nbco_run_host2", "nbco_step_host2",
     "nbco_fmm2_levels", "nbco_fmm2_get_info", "nbco_fmm2_get_tree", "nbco_fmm2_get_phase_ms",
     "nbco_init_ga2", "nbco_init_kv2", "nbco_beam_params2", "nbco_state_read2", "nbco_state_write2",
-    "nbco_peer_export", "nbco_peer_attach", "nbco_peer_commit", "nbco_peer_barrier", "nbco_peer_gather", "nbco_peer_detach",
+    "nbco_peer_export", "nbco_peer_attach", "nbco_peer_attach_local", "nbco_peer_commit", "nbco_peer_barrier", "nbco_peer_gather", "nbco_peer_detach",
     "nbco_shard_range", "nbco_init_ga", "nbco_init_test_cube", "nbco_state_read", "nbco_state_write", "nbco_free",
 ]
 
@@ -92,6 +92,7 @@ def _load():
     L.nbco_free.argtypes = [vp]
     L.nbco_peer_export.argtypes = [vp, i64, vp]
     L.nbco_peer_attach.argtypes = [vp, C.c_int32, vp]
+    L.nbco_peer_attach_local.argtypes = [vp, C.c_int32, vp]
     L.nbco_peer_commit.argtypes = [vp]
     L.nbco_peer_barrier.argtypes = [vp]
     L.nbco_peer_gather.argtypes = [vp, vp, i64]
@@ -338,6 +339,9 @@ class Context:
 
     def peer_attach(self, rank, handles):
         _check(lib.nbco_peer_attach(self._h, rank, _hp(np.ascontiguousarray(handles, np.uint8))))
+
+    def peer_attach_local(self, rank, other):
+        _check(lib.nbco_peer_attach_local(self._h, rank, other._h))
 
     def peer_commit(self):
         _check(lib.nbco_peer_commit(self._h))

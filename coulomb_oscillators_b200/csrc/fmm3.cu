@@ -614,7 +614,9 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 			NBCO_TRY(peer_barrier(ctx)); // the position mirrors are rewritten below
 			pulled = true;
 		}
-		NBCO_TRY(kd_build(ctx, p.kd, d_pos, p.ev[PH_KDBOTTOM], pr, pg));
+		// small trees: fewer shared-memory kd blocks than ranks -> every rank builds everything (all positions are here)
+		const int bg = pg <= p.kd.lt ? pg : 0;
+		NBCO_TRY(kd_build(ctx, p.kd, d_pos, p.ev[PH_KDBOTTOM], bg ? pr : 0, bg));
 		NBCO_CUDA(cudaEventRecord(p.ev[PH_PERMUTE], st));
 		if (c.unsort)
 			spos = p.kd.spos.as<float>();
@@ -675,6 +677,9 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 		const char *mode = getenv("NBCO_TRAVERSE");
 		if (n / c.world > (1ll << 22) && !(mode && !strcmp(mode, "queue"))) p.queue_blocks = 0;
 		if (mode && !strcmp(mode, "rounds")) p.queue_blocks = 0;
+		// one plain launch per round: cooperative grids do not overlap with other streams' kernels, which
+		// deadlocks several ranks emulated on ONE device against each other's barrier kernels (tests only)
+		if (mode && !strcmp(mode, "launches")) { p.queue_blocks = 0; p.coop_blocks = 0; }
 	}
 	if (p.queue_blocks > 0)
 	{
@@ -764,9 +769,11 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 		if (!ops) { set_error("order %d not instantiated", p.order); return NBCO_ERR_INVALID; }
 		int s = run_phases(*ops, ctx, p, d_pos, d_acc, d_param, fuse_elastic, do_build);
 		NBCO_TRY(s);
-		u32 h[6];
+		u32 h[6], perr = 0;
 		NBCO_CUDA(cudaMemcpyAsync(h, p.cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+		if (ctx->peer.active) NBCO_CUDA(cudaMemcpyAsync(&perr, (const char *)ctx->peer.pub.p + 512, 4, cudaMemcpyDeviceToHost, ctx->stream));
 		NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (perr) { set_error("peer barrier timed out: a rank did not arrive (results of this evaluation are invalid)"); return NBCO_ERR_CUDA; }
 		p.ev_valid = true;
 		p.rebuilt = rebuild;
 		for (int k = 0; k < PH_COUNT; ++k)

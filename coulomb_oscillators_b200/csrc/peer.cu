@@ -142,6 +142,30 @@ int nbco_peer_attach(nbco_ctx *ctx, int32_t peer_rank, const void *h_handles)
 	return NBCO_OK;
 }
 
+int nbco_peer_attach_local(nbco_ctx *ctx, int32_t peer_rank, nbco_ctx *other)
+// same process: no IPC, the published buffers of `other` are used directly (one process driving several GPUs,
+// or several ranks emulated on one device from different host threads -- tests/test_peer_gpu.py)
+{
+	if (!ctx || !other) { set_error("null argument"); return NBCO_ERR_INVALID; }
+	NBCO_CUDA(cudaSetDevice(ctx->cfg.device));
+	PeerState &ps = ctx->peer;
+	const PeerState &po = other->peer;
+	if (peer_rank < 0 || peer_rank >= ps.world || peer_rank == ps.me || po.me != peer_rank || !po.pubp[po.me] || po.n != ps.n || !ps.pubp[ps.me])
+	{
+		set_error("attach_local: export both contexts first (rank %d of %d, other is rank %d)", peer_rank, ps.world, po.me);
+		return NBCO_ERR_INVALID;
+	}
+	if (other->cfg.device != ctx->cfg.device)
+	{
+		cudaError_t e = cudaDeviceEnablePeerAccess(other->cfg.device, 0);
+		if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+		(void)cudaGetLastError();
+	}
+	ps.center[peer_rank] = po.center[po.me]; ps.mpole[peer_rank] = po.mpole[po.me]; ps.pubp[peer_rank] = po.pubp[po.me];
+	ps.opened[peer_rank] = false;
+	return NBCO_OK;
+}
+
 int nbco_peer_commit(nbco_ctx *ctx)
 {
 	if (!ctx) { set_error("null context"); return NBCO_ERR_INVALID; }

@@ -257,6 +257,9 @@ void nbco_shard_range(int64_t n, int32_t rank, int32_t world, int64_t *begin, in
  * ranges from their owners.  nbco_peer_gather leaves the full [pos | vel | acc] on every rank again. */
 int nbco_peer_export(nbco_ctx *ctx, int64_t n, void *h_handles192);
 int nbco_peer_attach(nbco_ctx *ctx, int32_t peer_rank, const void *h_handles192);
+/* same process instead of IPC: wire rank `peer_rank` = `other` directly (several GPUs driven by one process, or ranks
+ * emulated on one device from different host threads) */
+int nbco_peer_attach_local(nbco_ctx *ctx, int32_t peer_rank, nbco_ctx *other);
 int nbco_peer_commit(nbco_ctx *ctx);
 int nbco_peer_barrier(nbco_ctx *ctx);   /* barrier + host synchronisation; NBCO_ERR_CUDA if a rank did not arrive */
 int nbco_peer_gather(nbco_ctx *ctx, void *d_buf, int64_t n);

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# tests/test_peer_gpu.py emulates several ranks on ONE device: every rank's stream needs its own hardware queue,
+# or a rank's spinning barrier kernel blocks the kernels of the rank it waits for (default: 8 connections)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
