@@ -167,19 +167,19 @@ __device__ __forceinline__ int expand_pair(int kind, int2 np, int2 *out)
 // level-synchronous round.  Appends are aggregated per CTA: the three output counters (p2p list, m2l
 // list, next frontier) receive ONE atomic each per 256 classified pairs -- per-warp atomics on the same
 // three addresses serialise in L2 and dominated the big rounds (profiles/r01_notes.md).
-__device__ __forceinline__ void traverse_round(const TravArgs &a, int round, u32 (*wtot)[3], u32 *base, bool solo = false)
+__device__ __forceinline__ void traverse_round(const TravArgs &a, const int2 *__restrict__ front_in, int2 *__restrict__ front_out, int round,
+                                               u32 (*wtot)[3], u32 *base)
 {
 	u32 *cin = a.cnt + 2 + round % 3, *cout = a.cnt + 2 + (round + 1) % 3, *cnext = a.cnt + 2 + (round + 2) % 3;
 	if (blockIdx.x == 0 && threadIdx.x == 0) *cnext = 0; // nobody touches it during this round
 	const u32 nin = min(*(volatile u32 *)cin, a.cap_front);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	// solo: CTA 0 runs a small round alone (no grid barrier needed before the next one)
-	for (u32 w0 = solo ? 0u : blockIdx.x * blockDim.x; w0 < nin; w0 += solo ? blockDim.x : gridDim.x * blockDim.x)
+	for (u32 w0 = blockIdx.x * blockDim.x; w0 < nin; w0 += gridDim.x * blockDim.x)
 	{
 		const u32 w = w0 + threadIdx.x;
 		int kind = 0, flags = 0;
 		int2 np = make_int2(0, 0);
-		if (w < nin) { np = a.front_in[w]; kind = classify_pair(a, np, flags); }
+		if (w < nin) { np = front_in[w]; kind = classify_pair(a, np, flags); }
 		int2 kids[3];
 		const int nf = expand_pair(kind, np, kids);
 		// packed per-lane counts: bits 0..9 p2p, 10..19 m2l, 20..31 frontier entries
@@ -209,7 +209,7 @@ __device__ __forceinline__ void traverse_round(const TravArgs &a, int round, u32
 		if (kind == 2 && s2 < a.cap_m2l) a.m2l[s2] = tagged;
 		if (nf && s3 + nf > a.cap_front) a.cnt[5] = 1u; // sticky: a frontier did not fit
 		if (nf && s3 + nf <= a.cap_front)
-			for (int k = 0; k < nf; ++k) a.front_out[s3 + k] = kids[k];
+			for (int k = 0; k < nf; ++k) front_out[s3 + k] = kids[k];
 		__syncthreads(); // wtot / base are reused by the next chunk
 	}
 }
@@ -218,22 +218,22 @@ __global__ void __launch_bounds__(256) traverse_round_kernel(TravArgs a, int rou
 {
 	__shared__ u32 wtot[8][3];
 	__shared__ u32 base[3];
-	traverse_round(a, round, wtot, base);
+	traverse_round(a, a.front_in, a.front_out, round, wtot, base);
 }
 
 // all rounds in one cooperative launch: a grid-wide barrier replaces ~2L kernel boundaries (most rounds
 // classify a few thousand pairs and are dominated by launch and ramp-up time)
-__global__ void __launch_bounds__(256) traverse_all_kernel(TravArgs a, int2 *fa, int2 *fb, int max_rounds)
+__global__ void __launch_bounds__(256) traverse_all_kernel(const TravArgs a, int2 *fa, int2 *fb, int max_rounds)
 {
 	__shared__ u32 wtot[8][3];
 	__shared__ u32 base[3];
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	for (int r = 0; r < max_rounds; ++r)
 	{
-		a.front_in = (r & 1) ? fb : fa;
-		a.front_out = (r & 1) ? fa : fb;
+		// (the kernel parameters are never written: a modified copy would live in local memory, and the
+		// owner-indexed centre pointers are read with a dynamic index)
 		if (*(volatile u32 *)(a.cnt + 2 + r % 3) == 0) break; // uniform: the counter was final before the last barrier
-		traverse_round(a, r, wtot, base);
+		traverse_round(a, (r & 1) ? fb : fa, (r & 1) ? fa : fb, r, wtot, base);
 		grid.sync();
 	}
 }
