@@ -383,6 +383,231 @@ __global__ void traverse_queue_init_kernel(unsigned long long *q, u32 *cnt)
 	}
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Incremental traversal (evaluations between two tree rebuilds).  The kd partition and the node boxes are
+// fixed between rebuilds; only the centres of charge move, so the traversal of the previous evaluation is
+// almost the traversal of this one: a pair changes its fate only when its MAC test flips (measured: a few
+// thousand of ~6 M visited pairs per step at N = 2^24).  The full traversal RECORDS every visited pair in
+// one array V (frontier after frontier; the children of a split pair are contiguous) with a record
+// R = kind | flags << 3 | first child << 5.  A reuse evaluation then
+//   (1) re-classifies every recorded pair in ONE data-parallel pass and lists the pairs whose kind changed,
+//   (2) retires the recorded descendants of the changed pairs (tombstones; a small breadth-first walk over
+//       the child links on one CTA) and marks the surviving changed pairs as seeds (they keep their record slot: parents still link to them),
+//   (3) emits the interaction lists from the surviving records (data-parallel),
+//   (4) runs the ordinary level-synchronous traversal from the seeds only (a few short rounds).
+// The lists are the same sets as a traversal from the root: a recorded pair survives iff none of its ancestors
+// changed kind, and every changed pair is re-expanded from scratch.  tests/test_fmm_gpu.py compares the lists
+// with a from-the-root traversal (NBCO_TRAVERSE=rounds) and with the oracle after several steps.
+// -------------------------------------------------------------------------------------------------
+constexpr u32 kTomb = 7u;
+__device__ __forceinline__ u32 rec_pack(int kind, int flags, u32 child) { return (u32)kind | ((u32)flags << 3) | (child << 5); }
+
+// one round: frontier V[start, start + nin) (or, for the seeds of an update, V[idx[0 .. nin)]: a re-expanded pair keeps
+// its record slot, so that its parent's child link still reaches it) -> children appended at V[out0, ...)
+__device__ __forceinline__ void rec_round(const TravArgs &a, int2 *__restrict__ V, u32 *__restrict__ R, u32 start, u32 out0,
+                                          const u32 *__restrict__ idx, int round, u32 (*wtot)[3], u32 *base)
+{
+	u32 *cin = a.cnt + 2 + round % 3, *cout = a.cnt + 2 + (round + 1) % 3, *cnext = a.cnt + 2 + (round + 2) % 3;
+	if (blockIdx.x == 0 && threadIdx.x == 0) *cnext = 0;
+	const u32 nin = *(volatile u32 *)cin;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (u32 w0 = blockIdx.x * blockDim.x; w0 < nin; w0 += gridDim.x * blockDim.x)
+	{
+		const u32 w = w0 + threadIdx.x;
+		int kind = 0, flags = 0;
+		int2 np = make_int2(0, 0);
+		const u32 me = w < nin ? (idx ? idx[w] : start + w) : 0u;
+		if (w < nin) { np = V[me]; kind = classify_pair(a, np, flags); }
+		int2 kids[3];
+		const int nf = expand_pair(kind, np, kids);
+		const u32 mine = (kind == 1 ? 1u : 0u) | (kind == 2 ? 1u << 10 : 0u) | ((u32)nf << 20);
+		u32 incl = mine;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += v;
+		}
+		if (lane == 31) { wtot[warp][0] = incl & 1023u; wtot[warp][1] = (incl >> 10) & 1023u; wtot[warp][2] = incl >> 20; }
+		__syncthreads();
+		if (threadIdx.x < 3)
+		{
+			u32 tot = 0;
+			for (int i = 0; i < 8; ++i) tot += wtot[i][threadIdx.x];
+			u32 *c = threadIdx.x == 0 ? a.cnt + 0 : (threadIdx.x == 1 ? a.cnt + 1 : cout);
+			base[threadIdx.x] = tot ? atomicAdd(c, tot) : 0u;
+		}
+		__syncthreads();
+		const u32 excl = incl - mine;
+		u32 s1 = base[0] + (excl & 1023u), s2 = base[1] + ((excl >> 10) & 1023u), s3 = base[2] + (excl >> 20);
+		for (int i = 0; i < warp; ++i) { s1 += wtot[i][0]; s2 += wtot[i][1]; s3 += wtot[i][2]; }
+		const int2 tagged = make_int2(np.x | (flags << kFlagShift), np.y);
+		if (kind == 1 && s1 < a.cap_p2p) a.p2p[s1] = tagged;
+		if (kind == 2 && s2 < a.cap_m2l) a.m2l[s2] = tagged;
+		const bool fits = (unsigned long long)out0 + s3 + nf <= a.cap_front;
+		if (nf && !fits) a.cnt[5] = 1u; // sticky: V did not fit (the host grows it and repeats from the root)
+		if (nf && fits)
+			for (int k = 0; k < nf; ++k) V[out0 + s3 + k] = kids[k];
+		if (w < nin) R[me] = rec_pack(kind, flags, out0 + s3);
+		__syncthreads();
+	}
+}
+
+// rounds from the frontier V[cnt[11], cnt[11] + cnt[2]) until nothing is left; cnt[11] = entries of V afterwards
+__global__ void __launch_bounds__(256) traverse_rec_kernel(const TravArgs a, int2 *V, u32 *R, const u32 *seeds, int max_rounds)
+{
+	__shared__ u32 wtot[8][3];
+	__shared__ u32 base[3];
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	u32 start = *(volatile u32 *)(a.cnt + 11);
+	grid.sync(); // everybody has read the start before CTA 0 may store the end
+	for (int r = 0; r < max_rounds; ++r)
+	{
+		const u32 nin = *(volatile u32 *)(a.cnt + 2 + r % 3);
+		if (nin == 0) break;
+		if ((unsigned long long)start + nin > a.cap_front) { if (blockIdx.x == 0 && threadIdx.x == 0) a.cnt[5] = 1u; break; }
+		if (r == 0 && seeds)
+		{
+			// update: the seeds are scattered records, their children start the appended region
+			rec_round(a, V, R, 0u, start, seeds, r, wtot, base);
+			grid.sync();
+		}
+		else
+		{
+			rec_round(a, V, R, start, start + nin, nullptr, r, wtot, base);
+			grid.sync();
+			start += nin;
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) a.cnt[11] = start;
+}
+
+__global__ void traverse_rec_init_kernel(int2 *V, u32 *cnt)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0)
+	{
+		V[0] = make_int2(0, 0);
+		cnt[0] = 0; cnt[1] = 0; cnt[2] = 1; cnt[3] = 0; cnt[4] = 0; cnt[5] = 0; cnt[11] = 0; cnt[12] = 0;
+	}
+}
+
+__global__ void traverse_reuse_init_kernel(u32 *cnt)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0) { cnt[0] = 0; cnt[1] = 0; cnt[5] = 0; cnt[12] = 0; }
+}
+
+// (1) which recorded pairs change kind with the new centres?  (kinds 0 and 3 do not depend on the centres)
+__global__ void __launch_bounds__(256) reval_kernel(const TravArgs a, const int2 *__restrict__ V, const u32 *__restrict__ R,
+                                                    u32 *__restrict__ clist, u32 cap_c)
+{
+	const u32 count = a.cnt[11];
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+	{
+		const u32 k = R[i] & 7u;
+		if (k == kTomb || k == 0u || k == 3u) continue;
+		int flags;
+		const int nk = classify_pair(a, V[i], flags);
+		if ((u32)nk != k)
+		{
+			const u32 pos = atomicAdd(a.cnt + 12, 1u);
+			if (pos < cap_c) clist[pos] = i; else a.cnt[5] = 1u;
+		}
+	}
+}
+
+// (2) one CTA: retire the recorded subtrees of the changed pairs, then re-insert the surviving changed pairs as seeds
+__global__ void __launch_bounds__(1024) retire_kernel(const TravArgs a, int2 *__restrict__ V, u32 *__restrict__ R,
+                                                      const u32 *__restrict__ clist, u32 *__restrict__ bq, u32 cap_q)
+{
+	__shared__ u32 s_head, s_tail, s_seeds;
+	const u32 nc = a.cnt[12];
+	if (threadIdx.x == 0) { s_head = 0; s_tail = 0; s_seeds = 0; }
+	__syncthreads();
+	for (u32 c = threadIdx.x; c < nc; c += blockDim.x)
+	{
+		const u32 rec = R[clist[c]], k = rec & 7u;
+		if (k >= 3u && k <= 5u)
+		{
+			const u32 nch = k == 3u ? 3u : 2u, pos = atomicAdd(&s_tail, nch);
+			for (u32 j = 0; j < nch; ++j) if (pos + j < cap_q) bq[pos + j] = (rec >> 5) + j; else a.cnt[5] = 1u;
+		}
+	}
+	__syncthreads();
+	for (;;)
+	{
+		const u32 lo = s_head, hi = min(s_tail, cap_q);
+		__syncthreads();
+		if (lo >= hi) break;
+		for (u32 q = lo + threadIdx.x; q < hi; q += blockDim.x)
+		{
+			const u32 j = bq[q], rec = R[j], k = rec & 7u;
+			R[j] = (rec & ~7u) | kTomb;
+			if (k >= 3u && k <= 5u)
+			{
+				const u32 nch = k == 3u ? 3u : 2u, pos = atomicAdd(&s_tail, nch);
+				for (u32 t = 0; t < nch; ++t) if (pos + t < cap_q) bq[pos + t] = (rec >> 5) + t; else a.cnt[5] = 1u;
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) s_head = hi;
+		__syncthreads();
+	}
+	// changed pairs that were not retired as somebody's descendant start a fresh expansion
+	for (u32 c = threadIdx.x; c < nc; c += blockDim.x)
+	{
+		const u32 i = clist[c], rec = R[i];
+		if ((rec & 7u) == kTomb) continue;
+		R[i] = (rec & ~7u) | kTomb;   // not emitted; the traversal rewrites this record in place
+		const u32 pos = atomicAdd(&s_seeds, 1u);
+		if (pos < cap_q) bq[pos] = i; else a.cnt[5] = 1u; // the walk is over: its queue now holds the seed list
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) { a.cnt[2] = s_seeds; a.cnt[3] = 0; a.cnt[4] = 0; }
+}
+
+// (3) the lists of the surviving records
+__global__ void __launch_bounds__(256) emit_kernel(const TravArgs a, const int2 *__restrict__ V, const u32 *__restrict__ R)
+{
+	__shared__ u32 wtot[8][2];
+	__shared__ u32 base[2];
+	const u32 count = a.cnt[11];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (u32 i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x)
+	{
+		const u32 i = i0 + threadIdx.x;
+		const u32 rec = i < count ? R[i] : 0u, k = rec & 7u;
+		const u32 mine = (k == 1u ? 1u : 0u) | (k == 2u ? 1u << 16 : 0u);
+		u32 incl = mine;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += v;
+		}
+		if (lane == 31) { wtot[warp][0] = incl & 0xffffu; wtot[warp][1] = incl >> 16; }
+		__syncthreads();
+		if (threadIdx.x < 2)
+		{
+			u32 tot = 0;
+			for (int w = 0; w < 8; ++w) tot += wtot[w][threadIdx.x];
+			base[threadIdx.x] = tot ? atomicAdd(a.cnt + threadIdx.x, tot) : 0u;
+		}
+		__syncthreads();
+		const u32 excl = incl - mine;
+		u32 s1 = base[0] + (excl & 0xffffu), s2 = base[1] + (excl >> 16);
+		for (int w = 0; w < warp; ++w) { s1 += wtot[w][0]; s2 += wtot[w][1]; }
+		if (k == 1u || k == 2u)
+		{
+			const int2 np = V[i];
+			const int2 tagged = make_int2(np.x | (int)(((rec >> 3) & 3u) << kFlagShift), np.y);
+			if (k == 1u && s1 < a.cap_p2p) a.p2p[s1] = tagged;
+			if (k == 2u && s2 < a.cap_m2l) a.m2l[s2] = tagged;
+		}
+		__syncthreads();
+	}
+}
+
 __global__ void traverse_init_kernel(int2 *front, u32 *cnt)
 {
 	if (threadIdx.x == 0 && blockIdx.x == 0)
@@ -498,6 +723,9 @@ struct FmmPlan
 	int coop_blocks = -1; // grid of the cooperative traversal kernel (0 = not available)
 	int queue_blocks = 0; // grid of the work-queue traversal kernel (0 = use the rounds)
 	bool queue_clean = false; // frontA holds nothing but the empty-slot sentinel
+	int rec_blocks = 0;       // grid of the recording traversal kernel (0 = incremental traversal unavailable)
+	bool rec_valid = false;   // V / R (frontA / frontB) describe the traversal of the previous evaluation
+	float rec_radius = 0.f; int rec_m2l_first = -1, rec_rank = -1, rec_world = -1;
 };
 
 static int plan_levels(int64_t n, int order, float dens, int max_level)
@@ -544,8 +772,8 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	}
 	NBCO_TRY(p.p2p.reserve(8 * (size_t)p.cap_list)); NBCO_TRY(p.m2l.reserve(8 * (size_t)p.cap_list));
 	NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
-	p.queue_clean = false;
-	NBCO_TRY(p.cnt.reserve(64)); NBCO_TRY(p.mfac.reserve(4 * 2 * 40));
+	p.queue_clean = false; p.rec_valid = false;
+	NBCO_TRY(p.cnt.reserve(128)); NBCO_TRY(p.mfac.reserve(4 * 2 * 40));
 	// MAC factor table: M = pow(mult / N, 1/(3p+6)) evaluated with the host libm like the
 	// reference CPU path (:410); a node of level l holds floor(n/2^l) or floor(n/2^l)+1 particles
 	float tab[2 * 32];
@@ -674,15 +902,48 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 			p.queue_blocks = ctx->sm_count * std::min(per_sm_q, 2);
 		// the work queue wins while a rank visits a moderate number of pairs (measured: 0.10 vs 0.15 ms at 64 k
 		// particles, 0.72 vs 0.41 ms at 16 M on one GPU); NBCO_TRAVERSE=rounds|queue overrides
+		int per_sm_r = 0;
+		if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, traverse_rec_kernel, 256, 0) == cudaSuccess && per_sm_r > 0)
+			p.rec_blocks = ctx->sm_count * std::min(per_sm_r, 4);
 		const char *mode = getenv("NBCO_TRAVERSE");
+		if (mode && (!strcmp(mode, "rounds") || !strcmp(mode, "queue") || !strcmp(mode, "launches"))) p.rec_blocks = 0;
 		if (n / c.world > (1ll << 22) && !(mode && !strcmp(mode, "queue"))) p.queue_blocks = 0;
 		if (mode && !strcmp(mode, "rounds")) p.queue_blocks = 0;
 		// one plain launch per round: cooperative grids do not overlap with other streams' kernels, which
 		// deadlocks several ranks emulated on ONE device against each other's barrier kernels (tests only)
 		if (mode && !strcmp(mode, "launches")) { p.queue_blocks = 0; p.coop_blocks = 0; }
 	}
-	if (p.queue_blocks > 0)
+	// incremental traversal (default; NBCO_TRAVERSE=rounds|queue|launches select a from-the-root kernel instead)
+	const bool incremental = p.rec_blocks > 0 && c.tree_steps > 1 && !c.unsort;
+	if (incremental)
 	{
+		int2 *V = p.frontA.as<int2>();
+		u32 *R = p.frontB.as<u32>(), *clist = R + p.cap_front;
+		const u32 half = p.cap_front / 2;
+		const bool reuse = p.rec_valid && !rebuild && p.rec_radius == c.radius && p.rec_m2l_first == c.m2l_first
+		                   && p.rec_rank == c.rank && p.rec_world == c.world;
+		p.queue_clean = false;
+		if (!reuse)
+		{
+			traverse_rec_init_kernel<<<1, 32, 0, st>>>(V, a.cnt); LAUNCHED(ctx);
+		}
+		else
+		{
+			traverse_reuse_init_kernel<<<1, 32, 0, st>>>(a.cnt); LAUNCHED(ctx);
+			reval_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(a, V, R, clist, half); LAUNCHED(ctx);
+			retire_kernel<<<1, 1024, 0, st>>>(a, V, R, clist, clist + half, half); LAUNCHED(ctx);
+			emit_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(a, V, R); LAUNCHED(ctx);
+		}
+		int max_rounds = rounds;
+		const u32 *seeds = reuse ? clist + half : nullptr;
+		void *args[] = {&a, &V, &R, &seeds, &max_rounds};
+		NBCO_CUDA(cudaLaunchCooperativeKernel((void *)traverse_rec_kernel, dim3(p.rec_blocks), dim3(256), args, 0, st));
+		LAUNCHED(ctx);
+		p.rec_valid = true; p.rec_radius = c.radius; p.rec_m2l_first = c.m2l_first; p.rec_rank = c.rank; p.rec_world = c.world;
+	}
+	else if (p.queue_blocks > 0)
+	{
+		p.rec_valid = false;
 		// the queue lives in frontA; it is all-SENT between evaluations (consumers restore what they take)
 		unsigned long long *q = p.frontA.as<unsigned long long>();
 		if (!p.queue_clean)
@@ -698,7 +959,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	else if (p.coop_blocks > 0)
 	{
 		traverse_init_kernel<<<1, 32, 0, st>>>(p.frontA.as<int2>(), a.cnt); LAUNCHED(ctx);
-		p.queue_clean = false;
+		p.queue_clean = false; p.rec_valid = false;
 		int2 *fa = p.frontA.as<int2>(), *fb = p.frontB.as<int2>();
 		int max_rounds = rounds;
 		void *args[] = {&a, &fa, &fb, &max_rounds};
@@ -708,7 +969,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	else
 	{
 		traverse_init_kernel<<<1, 32, 0, st>>>(p.frontA.as<int2>(), a.cnt); LAUNCHED(ctx);
-		p.queue_clean = false;
+		p.queue_clean = false; p.rec_valid = false;
 		for (int r = 0; r < rounds; ++r)
 		{
 			a.front_in = (r & 1) ? p.frontB.as<int2>() : p.frontA.as<int2>();
@@ -800,7 +1061,7 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 		p.cap_list *= 2; p.cap_front = p.cap_list;
 		NBCO_TRY(p.p2p.reserve(8 * (size_t)p.cap_list)); NBCO_TRY(p.m2l.reserve(8 * (size_t)p.cap_list));
 		NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
-		p.queue_clean = false;
+		p.queue_clean = false; p.rec_valid = false;
 		if (!ctx->cfg.unsort) do_build = false;
 	}
 	set_error("interaction lists exceed capacity (%lld p2p, %lld m2l)", (long long)p.p2p_n, (long long)p.m2l_n);

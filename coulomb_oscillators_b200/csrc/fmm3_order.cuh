@@ -310,6 +310,7 @@ l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__
 
 
 constexpr int kTopLevels = 7; // levels 0..7 of the upward / 2..8 of the downward pass run in one CTA
+constexpr int kWideLevel = 1 << 16; // nodes of one rank at a level from which the level gets its own launch
 constexpr int kSubLevels = 7; // deeper levels: chunks of 7 levels, one CTA per subtree (128 nodes at its widest level)
 
 template <int P>
@@ -329,9 +330,17 @@ struct OrderImpl
 		else if (mlt_max <= 16) leaf_p2m_group_kernel<P, 16><<<grid_for(16ll * count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
 		else leaf_p2m_group_kernel<P, 32><<<grid_for(32ll * count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
 		++ctx->launches;
-		// levels L-1 .. max(kTopLevels + 1, g) in chunks of kSubLevels levels, one CTA per subtree of a chunk
+		// levels L-1 .. max(kTopLevels + 1, g): a level with many nodes of this rank gets its own launch (bandwidth-bound,
+		// fully parallel); the smaller ones run in chunks of kSubLevels levels, one CTA per subtree of a chunk
+		// (latency-bound: a launch per level would cost more than the work)
 		const int lstop = std::max(kTopLevels + 1, g);
-		for (int lhi = L - 1; lhi >= lstop; lhi -= kSubLevels)
+		int lhi = L - 1;
+		for (; lhi >= lstop && (1 << (lhi - g)) >= kWideLevel; --lhi)
+		{
+			const int cnt = 1 << (lhi - g);
+			m2m_level_kernel<P><<<(cnt + 127) / 128, 128, 0, st>>>(t, n, lhi, r << (lhi - g), cnt); ++ctx->launches;
+		}
+		for (; lhi >= lstop; lhi -= kSubLevels)
 		{
 			const int llo = std::max(lhi - kSubLevels + 1, lstop);
 			m2m_sub_kernel<P><<<1 << (llo - g), 128, 0, st>>>(t, n, lhi, llo, r << (llo - g)); ++ctx->launches;
@@ -350,12 +359,23 @@ struct OrderImpl
 		if (L >= 2)
 		{
 			l2l_top_kernel<P><<<1, 256, 0, st>>>(t, 2, std::min(L, kTopLevels + 1)); ++ctx->launches;
-			// child levels kTopLevels + 2 .. L in chunks of kSubLevels, one CTA per subtree of the rank's own part
-			for (int lf = kTopLevels + 2; lf <= L; lf += kSubLevels)
+			// child levels kTopLevels + 2 .. L: chunks of kSubLevels levels (one CTA per subtree of the rank's own part)
+			// while a level is small, one launch per level once it is wide (see upward())
+			int lf = kTopLevels + 2;
+			for (; lf <= L; lf += kSubLevels)
 			{
-				const int ll = std::min(lf + kSubLevels - 1, L), lroot = lf - 1;
+				int ll = std::min(lf + kSubLevels - 1, L);
+				while (ll >= lf && ll >= g && (1 << (ll - g)) >= kWideLevel) --ll; // leave the wide levels to the loop below
+				if (ll < lf) break;
+				const int lroot = lf - 1;
 				const int first = lroot >= g ? r << (lroot - g) : r >> (g - lroot), count = lroot >= g ? 1 << (lroot - g) : 1;
 				l2l_sub_kernel<P><<<count, 128, 0, st>>>(t, lf, ll, first); ++ctx->launches;
+				if (ll < lf + kSubLevels - 1) { lf = ll + 1; break; }
+			}
+			for (int l = lf; l <= L; ++l)
+			{
+				const int first = l >= g ? r << (l - g) : r >> (g - l), count = l >= g ? 1 << (l - g) : 1;
+				l2l_level_kernel<P><<<(count + 127) / 128, 128, 0, st>>>(t, l, first, count); ++ctx->launches;
 			}
 		}
 		if (ev_l2p) cudaEventRecord(ev_l2p, st);

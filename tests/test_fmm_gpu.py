@@ -170,6 +170,44 @@ def test_fmm_tree_reuse_between_rebuilds():
     assert np.abs(s[1] - o[1]).max() <= 1e-4 * np.abs(o[1]).max()
 
 
+@pytest.mark.parametrize("n,order,m2l_first,dt", [(50000, 3, 1, 5e-4), (200000, 3, 0, 5e-3), (30000, 5, 1, 2e-2)])
+def test_incremental_traversal_gives_the_same_lists(n, order, m2l_first, dt, monkeypatch):
+    """Between rebuilds the traversal is updated from the previous one (re-classify every recorded pair, retire the
+    subtrees of the pairs whose MAC flipped, re-expand those): after every step the lists must be the same SETS as a
+    traversal from the root, and equal to the oracle's.  Large dt: many flips per step."""
+    import torch
+    st = nb.init_ga(n)
+    par = nb.default_param(n)
+    dpar = torch.from_numpy(par).cuda()
+    ev = nb.EVAL_COULOMB_FMM3_KD
+
+    def make():
+        c = nb.Context(order=order, unsort=0, tree_steps=8, m2l_first=m2l_first)
+        b = torch.zeros(9 * n, dtype=torch.float32, device="cuda")
+        b[:6 * n] = torch.from_numpy(st.ravel()).cuda()
+        c.compute_force(ev, b.data_ptr(), n, dpar.data_ptr())
+        return c, b
+
+    ci, bi = make()                                  # incremental (default)
+    monkeypatch.setenv("NBCO_TRAVERSE", "rounds")
+    cr, br = make()                                  # from the root every time
+    monkeypatch.delenv("NBCO_TRAVERSE")
+    assert all(np.array_equal(x, y) for x, y in zip(ci.fmm_lists(), cr.fmm_lists()))
+    changed = 0
+    prev = ci.fmm_lists()
+    for step in range(7):
+        ci.integrate(nb.LEAPFROG, ev, bi.data_ptr(), n, dpar.data_ptr(), dt, 1)
+        # same state for the from-the-root context: lists depend on the positions only
+        br.copy_(bi)
+        cr.compute_force(ev, br.data_ptr(), n, dpar.data_ptr())
+        Li, Lr = ci.fmm_lists(), cr.fmm_lists()
+        assert ci.fmm_info().rebuilt == 0 and cr.fmm_info().rebuilt == 0
+        assert np.array_equal(Li[0], Lr[0]) and np.array_equal(Li[1], Lr[1]), step
+        changed += int(not (np.array_equal(Li[0], prev[0]) and np.array_equal(Li[1], prev[1])))
+        prev = Li
+    assert changed > 0   # the lists did move, i.e. the update path was exercised
+
+
 def test_fmm_full_size_properties():
     """N = 2^22 (beyond what the oracle finishes in seconds): structural properties of the result"""
     import torch
