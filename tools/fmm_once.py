@@ -1,4 +1,4 @@
-"""One rebuild evaluation + one reuse evaluation of the FMM (for ncu launch lists)."""
+"""One rebuild evaluation + two reuse evaluations of the FMM (for ncu launch lists)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -11,5 +11,5 @@ buf[:6 * n] = torch.from_numpy(st.ravel()).cuda()
 par = torch.from_numpy(nb.default_param(n)).cuda()
 ctx = nb.Context(order=p, unsort=0, tree_steps=8)
 ctx.compute_force(nb.EVAL_COULOMB_FMM3_KD, buf.data_ptr(), n, par.data_ptr())
-ctx.integrate(nb.LEAPFROG, nb.EVAL_COULOMB_FMM3_KD, buf.data_ptr(), n, par.data_ptr(), 5e-4, 1)
+ctx.integrate(nb.LEAPFROG, nb.EVAL_COULOMB_FMM3_KD, buf.data_ptr(), n, par.data_ptr(), 5e-4, 2)
 print("ok", ctx.fmm_info().kernel_launches, ctx.fmm_phase_ms())
