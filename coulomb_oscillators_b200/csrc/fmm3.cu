@@ -479,8 +479,9 @@ __global__ void __launch_bounds__(256) traverse_rec_kernel(const TravArgs a, int
 			grid.sync();
 			start += nin;
 		}
+		if (blockIdx.x == 0 && threadIdx.x == 0) a.cnt[15] = (u32)r + 1u; // rounds run (diagnostics)
 	}
-	if (blockIdx.x == 0 && threadIdx.x == 0) a.cnt[11] = start;
+	if (blockIdx.x == 0 && threadIdx.x == 0) { a.cnt[11] = start; }
 }
 
 __global__ void traverse_rec_init_kernel(int2 *V, u32 *cnt)
@@ -494,7 +495,7 @@ __global__ void traverse_rec_init_kernel(int2 *V, u32 *cnt)
 
 __global__ void traverse_reuse_init_kernel(u32 *cnt)
 {
-	if (threadIdx.x == 0 && blockIdx.x == 0) { cnt[0] = 0; cnt[1] = 0; cnt[5] = 0; cnt[12] = 0; }
+	if (threadIdx.x == 0 && blockIdx.x == 0) { cnt[0] = 0; cnt[1] = 0; cnt[5] = 0; cnt[12] = 0; cnt[13] = 0; cnt[14] = 0; cnt[15] = 0; cnt[16] = 0; cnt[17] = 0; cnt[18] = 0; cnt[19] = 0; }
 }
 
 // (1) which recorded pairs change kind with the new centres?  (kinds 0 and 3 do not depend on the centres)
@@ -516,54 +517,85 @@ __global__ void __launch_bounds__(256) reval_kernel(const TravArgs a, const int2
 	}
 }
 
-// (2) one CTA: retire the recorded subtrees of the changed pairs, then re-insert the surviving changed pairs as seeds
-__global__ void __launch_bounds__(1024) retire_kernel(const TravArgs a, int2 *__restrict__ V, u32 *__restrict__ R,
-                                                      const u32 *__restrict__ clist, u32 *__restrict__ bq, u32 cap_q)
+// (2) retire the recorded subtrees of the changed pairs (a breadth-first walk over the child links: measured 4-6
+// rounds, ~30 k records per step at N = 2^24), then list the surviving changed pairs as seeds.  Cooperative launch:
+// a grid barrier per round.  cnt[14] = walk queue tail, cnt[16] = seeds.
+__device__ __forceinline__ u32 warp_reserve(u32 *counter, u32 count)
 {
-	__shared__ u32 s_head, s_tail, s_seeds;
+	const int lane = threadIdx.x & 31;
+	u32 incl = count;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += v;
+	}
+	const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+	u32 base = 0;
+	if (lane == 31 && total) base = atomicAdd(counter, total);
+	base = __shfl_sync(0xffffffffu, base, 31);
+	return base + incl - count;
+}
+
+__global__ void __launch_bounds__(256) retire_kernel(const TravArgs a, u32 *__restrict__ R, const u32 *__restrict__ clist,
+                                                     u32 *__restrict__ bq, u32 cap_q)
+{
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const u32 nc = a.cnt[12];
-	if (threadIdx.x == 0) { s_head = 0; s_tail = 0; s_seeds = 0; }
-	__syncthreads();
-	for (u32 c = threadIdx.x; c < nc; c += blockDim.x)
+	const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+	const u32 nc_pad = (nc + 31u) & ~31u; // whole warps stay in the loops (warp_reserve shuffles)
+	// three rotating frontier counters (cnt[17..19]) like the traversal rounds: the size of round r is final at the
+	// barrier, the pushes of round r count into the next one, the one after is cleared -- no CTA ever reads a
+	// counter that a faster CTA is already adding to
+	for (u32 c = gtid; c < nc_pad; c += gstride)
 	{
-		const u32 rec = R[clist[c]], k = rec & 7u;
-		if (k >= 3u && k <= 5u)
-		{
-			const u32 nch = k == 3u ? 3u : 2u, pos = atomicAdd(&s_tail, nch);
-			for (u32 j = 0; j < nch; ++j) if (pos + j < cap_q) bq[pos + j] = (rec >> 5) + j; else a.cnt[5] = 1u;
-		}
+		u32 rec = 0, nch = 0;
+		if (c < nc) { rec = R[clist[c]]; const u32 k = rec & 7u; nch = (k >= 3u && k <= 5u) ? (k == 3u ? 3u : 2u) : 0u; }
+		const u32 pos = warp_reserve(a.cnt + 17, nch);
+		for (u32 j = 0; j < nch; ++j) if (pos + j < cap_q) bq[pos + j] = (rec >> 5) + j; else a.cnt[5] = 1u;
 	}
-	__syncthreads();
-	for (;;)
+	grid.sync();
+	u32 head = 0;
+	for (int r = 0;; ++r)
 	{
-		const u32 lo = s_head, hi = min(s_tail, cap_q);
-		__syncthreads();
-		if (lo >= hi) break;
-		for (u32 q = lo + threadIdx.x; q < hi; q += blockDim.x)
+		u32 *cin = a.cnt + 17 + r % 3, *cout = a.cnt + 17 + (r + 1) % 3, *cnext = a.cnt + 17 + (r + 2) % 3;
+		const u32 span = *(volatile u32 *)cin;
+		if (span == 0 || head + span > cap_q) break; // uniform
+		if (gtid == 0) *cnext = 0;
+		const u32 out0 = head + span, span_pad = (span + 31u) & ~31u;
+		for (u32 q = gtid; q < span_pad; q += gstride)
 		{
-			const u32 j = bq[q], rec = R[j], k = rec & 7u;
-			R[j] = (rec & ~7u) | kTomb;
-			if (k >= 3u && k <= 5u)
+			u32 rec = 0, nch = 0;
+			if (q < span)
 			{
-				const u32 nch = k == 3u ? 3u : 2u, pos = atomicAdd(&s_tail, nch);
-				for (u32 t = 0; t < nch; ++t) if (pos + t < cap_q) bq[pos + t] = (rec >> 5) + t; else a.cnt[5] = 1u;
+				const u32 j = bq[head + q];
+				rec = R[j];
+				const u32 k = rec & 7u;
+				R[j] = (rec & ~7u) | kTomb;
+				nch = (k >= 3u && k <= 5u) ? (k == 3u ? 3u : 2u) : 0u;
 			}
+			const u32 pos = out0 + warp_reserve(cout, nch);
+			for (u32 t = 0; t < nch; ++t) if (pos + t < cap_q) bq[pos + t] = (rec >> 5) + t; else a.cnt[5] = 1u;
 		}
-		__syncthreads();
-		if (threadIdx.x == 0) s_head = hi;
-		__syncthreads();
+		if (gtid == 0) { a.cnt[13] += 1u; a.cnt[14] = out0; }
+		grid.sync();
+		head = out0;
 	}
-	// changed pairs that were not retired as somebody's descendant start a fresh expansion
-	for (u32 c = threadIdx.x; c < nc; c += blockDim.x)
+	// changed pairs that were not retired as somebody's descendant start a fresh expansion (in place: see rec_round)
+	for (u32 c = gtid; c < nc_pad; c += gstride)
 	{
-		const u32 i = clist[c], rec = R[i];
-		if ((rec & 7u) == kTomb) continue;
-		R[i] = (rec & ~7u) | kTomb;   // not emitted; the traversal rewrites this record in place
-		const u32 pos = atomicAdd(&s_seeds, 1u);
-		if (pos < cap_q) bq[pos] = i; else a.cnt[5] = 1u; // the walk is over: its queue now holds the seed list
+		u32 i = 0, want = 0;
+		if (c < nc)
+		{
+			i = clist[c];
+			const u32 rec = R[i];
+			if ((rec & 7u) != kTomb) { R[i] = (rec & ~7u) | kTomb; want = 1u; } // not emitted; the traversal rewrites the record
+		}
+		const u32 pos = warp_reserve(a.cnt + 16, want);
+		if (want) { if (pos < cap_q) bq[pos] = i; else a.cnt[5] = 1u; } // the walk is over: its queue now holds the seed list
 	}
-	__syncthreads();
-	if (threadIdx.x == 0) { a.cnt[2] = s_seeds; a.cnt[3] = 0; a.cnt[4] = 0; }
+	grid.sync();
+	if (gtid == 0) { a.cnt[2] = a.cnt[16]; a.cnt[3] = 0; a.cnt[4] = 0; }
 }
 
 // (3) the lists of the surviving records
@@ -931,7 +963,13 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 		{
 			traverse_reuse_init_kernel<<<1, 32, 0, st>>>(a.cnt); LAUNCHED(ctx);
 			reval_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(a, V, R, clist, half); LAUNCHED(ctx);
-			retire_kernel<<<1, 1024, 0, st>>>(a, V, R, clist, clist + half, half); LAUNCHED(ctx);
+			{
+				u32 *bq = clist + half;
+				u32 cap_q = half;
+				void *rargs[] = {&a, &R, &clist, &bq, &cap_q};
+				NBCO_CUDA(cudaLaunchCooperativeKernel((void *)retire_kernel, dim3(ctx->sm_count * 2), dim3(256), rargs, 0, st));
+				LAUNCHED(ctx);
+			}
 			emit_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(a, V, R); LAUNCHED(ctx);
 		}
 		int max_rounds = rounds;
@@ -1034,6 +1072,13 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 		NBCO_CUDA(cudaMemcpyAsync(h, p.cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
 		if (ctx->peer.active) NBCO_CUDA(cudaMemcpyAsync(&perr, (const char *)ctx->peer.pub.p + 512, 4, cudaMemcpyDeviceToHost, ctx->stream));
 		NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
+		if (getenv("NBCO_DEBUG_TRAV"))
+		{
+			u32 dbg[20];
+			cudaMemcpy(dbg, p.cnt.p, sizeof(dbg), cudaMemcpyDeviceToHost);
+			fprintf(stderr, "trav: p2p %u m2l %u records %u changed %u seeds %u retire-rounds %u retired %u rec-rounds %u\n", dbg[0], dbg[1], dbg[11],
+			        dbg[12], dbg[16], dbg[13], dbg[14], dbg[15]);
+		}
 		if (perr) { set_error("peer barrier timed out: a rank did not arrive (results of this evaluation are invalid)"); return NBCO_ERR_CUDA; }
 		p.ev_valid = true;
 		p.rebuilt = rebuild;
