@@ -211,6 +211,7 @@ void nbco_destroy(nbco_ctx *ctx)
 	fmm2_destroy(ctx);
 	ctx->pos4.release(); ctx->red.release(); ctx->h_state.release(); ctx->h_param.release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
+	if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_drift); cudaEventDestroy(ctx->ev_copied); }
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -384,6 +385,31 @@ int nbco_step_host(nbco_ctx *ctx, int scheme, int evaluator, float *h_buf, int64
 	const size_t vb = sizeof(float) * 3 * (size_t)n;
 	NBCO_CUDA(cudaMemcpyAsync(d_buf, h_buf, 3 * vb, cudaMemcpyHostToDevice, ctx->stream));
 	const float dtf = (float)dt;
+	// One leapfrog step whose evaluation does not permute the state: the positions are final after the drift, so
+	// their read-back (a third of the D2H traffic) runs on a second stream while the forces are computed.
+	const bool fmm = evaluator == NBCO_EVAL_FMM3_KD || evaluator == NBCO_EVAL_COULOMB_FMM3_KD;
+	const bool overlap = scheme == NBCO_LEAPFROG && nsteps == 1 && !ctx->peer.active && (!fmm || !fmm3_next_rebuilds(ctx, n));
+	if (overlap)
+	{
+		if (!ctx->copy_stream)
+		{
+			NBCO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+			NBCO_CUDA(cudaEventCreateWithFlags(&ctx->ev_drift, cudaEventDisableTiming));
+			NBCO_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+		}
+		float *pos = d_buf, *vel = d_buf + 3*n, *acc = d_buf + 6*n;
+		const float h = (float)((long double)dtf * 0.5L);
+		NBCO_TRY(kick_drift_launch(ctx, pos, vel, acc, h, h, false, dtf, n));      // K(1/2) D, like run_steps
+		NBCO_CUDA(cudaEventRecord(ctx->ev_drift, ctx->stream));
+		NBCO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_drift, 0));
+		NBCO_CUDA(cudaMemcpyAsync(h_buf, pos, vb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+		NBCO_CUDA(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+		NBCO_TRY(eval_dispatch(ctx, evaluator, pos, acc, n, d_param));             // F (reads pos only)
+		NBCO_TRY(step_launch(ctx, vel, acc, h, n));                                 // K(1/2)
+		NBCO_CUDA(cudaMemcpyAsync(h_buf + 3*n, vel, 2 * vb, cudaMemcpyDeviceToHost, ctx->stream));
+		NBCO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+		return sync(ctx);
+	}
 	NBCO_TRY(run_steps(ctx, scheme, evaluator, d_buf, n, d_param, dtf, nsteps));
 	NBCO_CUDA(cudaMemcpyAsync(h_buf, d_buf, 3 * vb, cudaMemcpyDeviceToHost, ctx->stream));
 	return sync(ctx);

@@ -77,6 +77,8 @@ struct nbco_ctx
 	nbco::DevBuf h_state;   // [pos|vel|acc] for nbco_eval_host / nbco_run_host
 	nbco::DevBuf h_param;
 	void *pinned = nullptr; size_t pinned_bytes = 0;
+	cudaStream_t copy_stream = nullptr;   // nbco_step_host: read-back of the positions overlaps the force evaluation
+	cudaEvent_t ev_drift = nullptr, ev_copied = nullptr;
 
 	nbco::FmmPlan *fmm = nullptr;
 	nbco::PeerState peer;
@@ -97,6 +99,7 @@ int kinetic_elastic_launch(nbco_ctx *ctx, const float *d_buf, int64_t n, const f
 // fmm3.cu
 int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const float *d_param, bool fuse_elastic);
 void fmm3_destroy(nbco_ctx *ctx);
+bool fmm3_next_rebuilds(nbco_ctx *ctx, int64_t n); // will the next FMM evaluation of n particles permute pos / vel?
 // peer.cu
 int peer_barrier(nbco_ctx *ctx);                                           // all ranks, on the context streams
 int peer_publish(nbco_ctx *ctx, const float *d_full, int which, int64_t n);  // own range of pos (0) / vel (1) -> published mirror

@@ -820,6 +820,15 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	return NBCO_OK;
 }
 
+bool fmm3_next_rebuilds(nbco_ctx *ctx, int64_t n)
+{
+	const nbco_config &c = ctx->cfg;
+	if (!ctx->fmm) return true;
+	const FmmPlan &p = *ctx->fmm;
+	if (p.n != n || p.order != c.order || p.dens != c.dens_inhom || p.max_level != c.max_level) return true;
+	return c.unsort || (p.counter % c.tree_steps == 0);
+}
+
 int fmm3_peer_buffers(nbco_ctx *ctx, int64_t n, void **center, void **mpole)
 {
 	NBCO_TRY(ensure_plan(ctx, n));

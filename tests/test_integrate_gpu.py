@@ -101,3 +101,36 @@ def test_energy_drift_fmm_no_worse_than_reference_algorithm():
     h1 = sum(ctx.energy(buf.data_ptr(), n, dpar.data_ptr()))
     assert abs(h0 - 1.9998) < 2e-3            # H(step 1) = 1.99980 in the survey's run
     assert abs(h1 - h0) / h0 < 3e-4           # reference p = 3: 4.4e-5 after 100, 2.7e-4 after 200 steps
+
+
+@pytest.mark.parametrize("evaluator", [nb.EVAL_COULOMB_DIRECT3, nb.EVAL_COULOMB_FMM3_KD])
+def test_step_host_matches_device_integration(evaluator):
+    """nbco_step_host (H2D, one step, D2H; the read-back of the positions overlaps the force evaluation on the steps
+    that do not rebuild the tree) called step by step = nbco_integrate on a resident state"""
+    import torch
+    n, steps = 30000, 10
+    st = nb.init_ga(n)
+    par = nb.default_param(n)
+    dpar = torch.from_numpy(par).cuda()
+    c1 = nb.Context(order=3, unsort=0, tree_steps=4)
+    b1 = torch.zeros(9 * n, dtype=torch.float32, device="cuda")
+    b1[:6 * n] = torch.from_numpy(st.ravel()).cuda()
+    c1.compute_force(evaluator, b1.data_ptr(), n, dpar.data_ptr())
+    h = torch.empty(9 * n, dtype=torch.float32).pin_memory()
+    h.copy_(b1.cpu())
+    c1.integrate(nb.LEAPFROG, evaluator, b1.data_ptr(), n, dpar.data_ptr(), 5e-4, steps)
+    want = b1.cpu().numpy().reshape(3, n, 3)
+    c2 = nb.Context(order=3, unsort=0, tree_steps=4)
+    if evaluator == nb.EVAL_COULOMB_FMM3_KD:
+        # same tree phase as c1: the state on the host is already in tree order, evaluation 0 has been done there
+        c2.eval_host(nb.EVAL_FMM3_KD, st[0].copy(), st[1].copy(), par)
+    for _ in range(steps):
+        c2.step_host(nb.LEAPFROG, evaluator, h.numpy(), n, par, 5e-4, 1)
+    got = h.numpy().reshape(3, n, 3)
+    if evaluator == nb.EVAL_COULOMB_DIRECT3:
+        assert np.array_equal(got, want)
+    else:
+        o = np.lexsort((want[0][:, 2], want[0][:, 1], want[0][:, 0]))
+        g = np.lexsort((got[0][:, 2], got[0][:, 1], got[0][:, 0]))
+        assert np.abs(got[0][g] - want[0][o]).max() <= 1e-6 * np.abs(want[0]).max()
+        assert np.abs(got[1][g] - want[1][o]).max() <= 1e-5 * np.abs(want[1]).max()
