@@ -151,11 +151,13 @@ __device__ __forceinline__ int owner_of(int64_t j, int64_t n, int l, unsigned lo
 __device__ __forceinline__ void self_p2p(float *f, const float *__restrict__ spos, int64_t j, int leaf,
                                          float x, float y, float z, int64_t n, int L, float eps2)
 {
-	const int64_t s0 = seg_start(n, leaf, L), s1 = seg_start(n, leaf + 1, L);
+	const int64_t s0 = seg_start(n, leaf, L);
+	const int cnt = (int)(seg_start(n, leaf + 1, L) - s0);
+	const float *__restrict__ lp = spos + 3 * s0; // 64-bit address once, small offsets below (the L2P kernel is issue-bound)
 	float ax = 0.f, ay = 0.f, az = 0.f;
-	for (int64_t k = s0; k < s1; ++k)
+	auto term = [&](int k)
 	{
-		const float dx = x - spos[3*k], dy = y - spos[3*k+1], dz = z - spos[3*k+2];
+		const float dx = x - lp[3*k], dy = y - lp[3*k+1], dz = z - lp[3*k+2];
 		float r2 = fmaf(dx, dx, eps2);
 		r2 = fmaf(dy, dy, r2);
 		r2 = fmaf(dz, dz, r2);
@@ -164,7 +166,11 @@ __device__ __forceinline__ void self_p2p(float *f, const float *__restrict__ spo
 		w = w * fmaf(-0.5f * r2 * w, w, 1.5f);
 		const float w3 = (w * w) * w;
 		ax = fmaf(dx, w3, ax); ay = fmaf(dy, w3, ay); az = fmaf(dz, w3, az);
-	}
+	};
+#pragma unroll
+	for (int k = 0; k < 8; ++k)
+		if (k < cnt) term(k);
+	for (int k = 8; k < cnt; ++k) term(k);
 	(void)j;
 	f[0] += ax; f[1] += ay; f[2] += az;
 }
