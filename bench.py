@@ -144,7 +144,7 @@ def run_ours(args):
     # (g, r): it builds, summarises, traverses and steps its own tree-order range; remote nodes and leaves are
     # read from their owners over NVLink peer memory inside the kernels, the ranks meet at a flag barrier in
     # peer memory (csrc/peer.cu).  NCCL only carries the IPC handles and the timing reduce.
-    from coulomb_oscillators_b200.parallel import fmm_leapfrog_peer, peer_setup
+    from coulomb_oscillators_b200.parallel import fmm_leapfrog_peer, fmm_leapfrog_sharded, peer_setup
     state = nb.init_ga(n)
     par = nb.default_param(n)
     ctx = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first, rank=rank, world=world)
@@ -161,14 +161,30 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    peer_ok = world > 1
     if world > 1:
-        peer_setup(ctx, n)
+        # peer memory needs CUDA IPC + P2P between the ranks' devices; if any rank cannot map the others, ALL ranks
+        # fall back to the replicated-tree mode (all-gather of the positions per step over NCCL)
+        try:
+            peer_setup(ctx, n)
+            flag = 1
+        except Exception as e:  # noqa: BLE001
+            print(f"rank {rank}: peer setup failed ({e}); using the replicated-tree mode", file=sys.stderr, flush=True)
+            flag = 0
+        t = torch.tensor([flag], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        peer_ok = bool(t.item())
+        if not peer_ok:
+            ctx = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first, rank=rank, world=world)
+            stream = torch.cuda.ExternalStream(ctx.stream)
 
     def run_steps(k):
         if world == 1:
             ctx.integrate(nb.LEAPFROG, ev, buf.data_ptr(), n, dpar.data_ptr(), dt, k)
-        else:
+        elif peer_ok:
             fmm_leapfrog_peer(ctx, buf, n, dpar.data_ptr(), dt, k, gather_final=False)
+        else:
+            fmm_leapfrog_sharded(ctx, buf, n, dpar.data_ptr(), dt, k)
 
     ctx.compute_force(ev, buf.data_ptr(), n, dpar.data_ptr())       # main3.cu:835-839
     run_steps(args.warmup)
@@ -215,7 +231,10 @@ def run_ours(args):
             for k in (0, 1, 2):
                 buf[3 * n * k + 3 * lo:3 * n * k + 3 * hi].copy_(hbuf[3 * n * k + 3 * lo:3 * n * k + 3 * hi], non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            fmm_leapfrog_peer(ctx_e, buf, n, dpar.data_ptr(), dt, 1, gather_final=False)
+            if peer_ok:
+                fmm_leapfrog_peer(ctx_e, buf, n, dpar.data_ptr(), dt, 1, gather_final=False)
+            else:
+                fmm_leapfrog_sharded(ctx_e, buf, n, dpar.data_ptr(), dt, 1, gather_final=False)
             for k in (0, 1, 2):
                 hbuf[3 * n * k + 3 * lo:3 * n * k + 3 * hi].copy_(buf[3 * n * k + 3 * lo:3 * n * k + 3 * hi], non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -239,7 +258,7 @@ def run_ours(args):
     # secondary metric (BASELINE config 4): 2D fp64 FMM under PEFRL, one GPU
     fmm2d = bench_fmm2d(nb, torch, local) if (args.fmm2d and world == 1) else None
 
-    if world > 1:
+    if world > 1 and peer_ok:
         ctx.peer_detach()
     if rank != 0:
         if world > 1:
@@ -284,7 +303,8 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"3D kd-tree FMM leapfrog, N={n}, p={order}, r=1, tree_steps=8, reference initGA ICs"
                                + (f", sharded over {world} GPUs (rank r owns the subtree of kd node (log2 N, r); remote nodes / "
-                                  f"leaves read over NVLink peer memory inside the kernels, flag barriers in peer memory)" if world > 1 else ""),
+                                  f"leaves read over NVLink peer memory inside the kernels, flag barriers in peer memory)" if world > 1 and peer_ok else "")
+                               + (f", sharded over {world} GPUs (replicated tree, all-gather of positions per step; peer setup failed)" if world > 1 and not peer_ok else ""),
                    "n": n, "order": order, "levels": int(info.levels), "p2p_pairs": int(info.p2p_pairs),
                    "m2l_pairs": int(info.m2l_pairs), "m2l_first": args.m2l_first,
                    "l2_hygiene": "inputs larger than L2 (state 36 B x N + tree slab)" if 36 * n > 126e6 else "working set may fit L2",
