@@ -221,6 +221,12 @@ int nbco_set_config(nbco_ctx *ctx, const nbco_config *cfg)
 	if (!ctx || !cfg) { set_error("null argument"); return NBCO_ERR_INVALID; }
 	NBCO_TRY(check_cfg(cfg));
 	if (cfg->device != ctx->cfg.device) { set_error("the device of a context cannot change"); return NBCO_ERR_INVALID; }
+	if (ctx->peer.active && (cfg->rank != ctx->cfg.rank || cfg->world != ctx->cfg.world || cfg->unsort || cfg->order != ctx->cfg.order
+	                         || cfg->max_level != ctx->cfg.max_level || cfg->dens_inhom != ctx->cfg.dens_inhom))
+	{
+		set_error("rank, world, order, levels and unsort = 0 are fixed while peers are attached (nbco_peer_detach first)");
+		return NBCO_ERR_INVALID;
+	}
 	ctx->cfg = *cfg;
 	return NBCO_OK;
 }
