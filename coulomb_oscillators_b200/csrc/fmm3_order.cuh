@@ -251,6 +251,42 @@ __global__ void __launch_bounds__(128) l2l_level_kernel(TreeData t, int lchild, 
 	if (i < count) l2l_node<P>(t, kd_beg(lchild) + first + i);
 }
 
+// wide levels, tuples of 16 floats (P <= 3): FOUR lanes per node, each moves one float4 of the parent's and of the child's
+// tuple (every request touches fully used sectors; with a thread per node each request touches 32 half-used ones and
+// the kernel is bound by memory latency: ncu issue active 6 %, profiles/r01_notes.md); the quads are exchanged by
+// shuffles and the shift is computed by all four lanes, each storing its own quad
+template <int P>
+__global__ void __launch_bounds__(128) l2l_level4_kernel(TreeData t, int lchild, int first, int count)
+{
+	static_assert(pad4<trl_off(P + 1)>() == 16, "four float4 per tuple");
+	const int gt = blockIdx.x * blockDim.x + threadIdx.x, i = gt >> 2, sub = gt & 3;
+	if (i >= count) return; // a whole group of four leaves together
+	const unsigned gmask = 0xFu << ((threadIdx.x & 31) & ~3);
+	const int child = kd_beg(lchild) + first + i, parent = (child - 1) >> 1;
+	float4 *dst = reinterpret_cast<float4 *>(t.local + (int64_t)child * t.sL);
+	const float4 qp = reinterpret_cast<const float4 *>(t.local + (int64_t)parent * t.sL)[sub];
+	const float4 qc = dst[sub];
+	const float4 cp = t.center[parent], cc = t.center[child];
+	float Lp[16], Lc[16], S[sym_off(P + 1)];
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+	{
+		Lp[4*q]   = __shfl_sync(gmask, qp.x, q, 4); Lp[4*q+1] = __shfl_sync(gmask, qp.y, q, 4);
+		Lp[4*q+2] = __shfl_sync(gmask, qp.z, q, 4); Lp[4*q+3] = __shfl_sync(gmask, qp.w, q, 4);
+		Lc[4*q]   = __shfl_sync(gmask, qc.x, q, 4); Lc[4*q+1] = __shfl_sync(gmask, qc.y, q, 4);
+		Lc[4*q+2] = __shfl_sync(gmask, qc.z, q, 4); Lc[4*q+3] = __shfl_sync(gmask, qc.w, q, 4);
+	}
+	S[0] = 0.f;
+	local_expand<P>(S, Lp);
+	l2l_acc<P>(Lc, S, cc.x - cp.x, cc.y - cp.y, cc.z - cp.z);
+	float4 out;
+	out.x = sub == 0 ? Lc[0] : (sub == 1 ? Lc[4] : (sub == 2 ? Lc[8]  : Lc[12]));
+	out.y = sub == 0 ? Lc[1] : (sub == 1 ? Lc[5] : (sub == 2 ? Lc[9]  : Lc[13]));
+	out.z = sub == 0 ? Lc[2] : (sub == 1 ? Lc[6] : (sub == 2 ? Lc[10] : Lc[14]));
+	out.w = sub == 0 ? Lc[3] : (sub == 1 ? Lc[7] : (sub == 2 ? Lc[11] : Lc[15]));
+	dst[sub] = out;
+}
+
 // child levels lfirst .. llast of the subtree under node (lfirst - 1, first + blockIdx.x), one CTA per subtree
 template <int P>
 __global__ void __launch_bounds__(128) l2l_sub_kernel(TreeData t, int lfirst, int llast, int first)
@@ -375,7 +411,11 @@ struct OrderImpl
 			for (int l = lf; l <= L; ++l)
 			{
 				const int first = l >= g ? r << (l - g) : r >> (g - l), count = l >= g ? 1 << (l - g) : 1;
-				l2l_level_kernel<P><<<(count + 127) / 128, 128, 0, st>>>(t, l, first, count); ++ctx->launches;
+				if constexpr (pad4<trl_off(P + 1)>() == 16)
+					l2l_level4_kernel<P><<<(4 * count + 127) / 128, 128, 0, st>>>(t, l, first, count);
+				else
+					l2l_level_kernel<P><<<(count + 127) / 128, 128, 0, st>>>(t, l, first, count);
+				++ctx->launches;
 			}
 		}
 		if (ev_l2p) cudaEventRecord(ev_l2p, st);
