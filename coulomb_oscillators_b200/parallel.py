@@ -111,7 +111,9 @@ def peer_setup(ctx, n, group=None):
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     assert ctx.cfg.rank == rank and ctx.cfg.world == world and ctx.cfg.unsort == 0
-    mine = torch.from_numpy(ctx.peer_export(n)).cuda()
+    mine = torch.from_numpy(np.ascontiguousarray(ctx.peer_export(n), np.uint8))
+    if "nccl" in str(dist.get_backend(group)):
+        mine = mine.cuda()
     every = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(every, mine, group=group)
     for q, h in enumerate(every):

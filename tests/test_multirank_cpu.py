@@ -62,3 +62,59 @@ def test_sharded_direct_sum_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+class _FakePeerCtx:
+    """records what peer_setup does to a context (the real one needs a GPU: tests/test_peer_gpu.py, tools/peer_check.py)"""
+
+    class _Cfg:
+        unsort = 0
+
+    def __init__(self, rank, world):
+        self.cfg = self._Cfg()
+        self.cfg.rank, self.cfg.world = rank, world
+        self.calls = []
+
+    def peer_export(self, n):
+        self.calls.append(("export", n))
+        return np.full(192, 10 + self.cfg.rank, np.uint8)       # a recognisable "handle block"
+
+    def peer_attach(self, q, handles):
+        self.calls.append(("attach", q, int(handles[0]), len(handles)))
+
+    def peer_commit(self):
+        self.calls.append(("commit",))
+
+    def peer_barrier(self):
+        self.calls.append(("barrier",))
+
+
+def _peer_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from coulomb_oscillators_b200.parallel import peer_setup
+    ctx = _FakePeerCtx(rank, world)
+    peer_setup(ctx, 12345)
+    dist.destroy_process_group()
+    q.put((rank, ctx.calls))
+
+
+def test_peer_setup_exchanges_every_handle_block_gloo_world2():
+    """every rank exports once, attaches the 192-byte block of every OTHER rank exactly once, commits, then meets the
+    others at the peer barrier"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        other = 1 - r
+        assert res[r] == [("export", 12345), ("attach", other, 10 + other, 192), ("commit",), ("barrier",)]
