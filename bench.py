@@ -213,6 +213,16 @@ def run_ours(args):
     launches = info.kernel_launches - l0
     totals, evals, rebuilds = ctx.fmm_phase_totals(reset=True)
     assert np.isfinite(buf[:6 * n].sum().item()), "state diverged"
+    steps_done = args.warmup + args.steps
+
+    # ---- parity on the TIMED state (not timed): FMM forces against the direct sum on sampled targets, and for
+    # N > 1 ranks the whole state against a single-rank run of the same steps ----
+    if world > 1 and peer_ok:
+        ctx.peer_gather(buf.data_ptr(), n)          # every rank: full [pos | vel | acc] of the sharded run
+    parity = parity_block(nb, torch, ctx if world == 1 else None, buf, n, order, dpar, local, args.m2l_first,
+                          state if (world > 1 and rank == 0) else None, steps_done, dt) if (rank == 0 or world == 1) else None
+    if world > 1:
+        dist.barrier()
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region, every step ----
     hbuf = torch.empty(9 * n, dtype=torch.float32).pin_memory()
@@ -297,6 +307,8 @@ def run_ours(args):
                 "step_hbm_frac": round(step_bytes * (args.steps / (ms * 1e-3)) / 1e9 / (world * peaks["hbm_gbs"]), 4)}
 
     cpu = cpu_baseline(n, order, args.m2l_first, bounded=True) if world == 1 else None
+    ref_gpu = reference_gpu_baseline(local) if (world == 1 and args.ref_gpu) else None
+    config1 = config1_direct_leg(nb, torch, local) if world == 1 else None
     out = {
         "metric": "3D FMM particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -309,7 +321,8 @@ def run_ours(args):
                    "m2l_pairs": int(info.m2l_pairs), "m2l_first": args.m2l_first,
                    "l2_hygiene": "inputs larger than L2 (state 36 B x N + tree slab)" if 36 * n > 126e6 else "working set may fit L2",
                    "e2e_copies": "every step: H2D [pos|vel|acc] from pinned memory + D2H of the same"},
-        "roofline": roofline, "phases": phases, "cpu_baseline": cpu,
+        "roofline": roofline, "phases": phases, "cpu_baseline": cpu, "parity": parity,
+        "rebuilds_per_step": round(rebuilds / max(evals, 1), 4), "reference_gpu_baseline": ref_gpu, "config1_direct_n8192": config1,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s",
                 "h2d_bytes_per_step": 36 * n, "d2h_bytes_per_step": 36 * n, "steps": e2e_steps},
         "gpu_launches": int(launches), "clocks": clocks,
@@ -321,6 +334,57 @@ def run_ours(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_block(nb, torch, ctx, buf, n, order, dpar, local, m2l_first, ic_state, steps_done, dt, shards=8, per_shard=512):
+    """Accuracy evidence on the state the timed steps produced (SURVEY.md section 8(d) "accuracy reporting"):
+      * Coulomb-only FMM forces at the final positions against nbco_force_direct3 on shards x per_shard sampled
+        targets (sharded direct-sum calls: cfg.rank/world select the target rows), metric = mean rel_diff1
+        (reductions.cuh:37-42; test_accuracy, main3.cu:139-182).  The reference's own class at p = 3, r = 1 on these
+        ICs is 0.06-0.11; bit-exact tree/list parity at this N is the job of
+        tests/test_fmm_gpu.py::test_fmm_headline_size_matches_live_reference.
+      * N > 1 ranks (ic_state given): positions / velocities of the sharded run against a single-rank run of the
+        same number of steps from the same initial conditions (max |diff| / max |value|)."""
+    out = {}
+    pos_ptr = buf.data_ptr()
+    ev_ctx = ctx if ctx is not None else nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=m2l_first)
+    a_fmm = torch.empty(3 * n, dtype=torch.float32, device="cuda")
+    if ctx is None:
+        work = buf.clone()                      # a fresh context sorts its input: keep the gathered state intact
+        pos_ptr = work.data_ptr()
+    ev_ctx.force_fmm3_kd(pos_ptr, a_fmm.data_ptr(), n, dpar.data_ptr())
+    a_dir = torch.zeros(3 * n, dtype=torch.float32, device="cuda")
+    w = max(n // per_shard, 1)
+    dctx = nb.Context(device=local)
+    rows = []
+    for k in range(shards):
+        r = min(w - 1, (k * w) // shards + (w // (2 * shards)))
+        dctx.set(rank=r, world=w)
+        dctx.force_direct3(pos_ptr, a_dir.data_ptr(), n, dpar.data_ptr())
+        b, e = nb.shard_range(n, r, w)
+        rows.append((b, e))
+    torch.cuda.synchronize()
+    idx = torch.cat([torch.arange(b, e, device="cuda") for b, e in rows])
+    f = a_fmm.view(n, 3)[idx].double()
+    d = a_dir.view(n, 3)[idx].double()
+    rel = ((f - d).pow(2).sum(1) / (d.pow(2).sum(1) + 1e-18)).sqrt()
+    out["fmm_vs_direct"] = {"targets": int(idx.numel()), "mean_rel_diff1": float(rel.mean().item()), "max_rel_diff1": float(rel.max().item()),
+                            "reference_class_p3_r1": [0.02, 0.2], "what": "Coulomb-only forces at the final positions of the timed run"}
+    if order == 3:
+        out["fmm_vs_direct"]["ok"] = bool(0.02 < out["fmm_vs_direct"]["mean_rel_diff1"] < 0.2)
+    if ic_state is not None:
+        c1 = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=m2l_first)
+        b1 = torch.empty(9 * n, dtype=torch.float32, device="cuda")
+        b1[:6 * n] = torch.from_numpy(ic_state.reshape(-1)).cuda()
+        c1.compute_force(nb.EVAL_COULOMB_FMM3_KD, b1.data_ptr(), n, dpar.data_ptr())
+        c1.integrate(nb.LEAPFROG, nb.EVAL_COULOMB_FMM3_KD, b1.data_ptr(), n, dpar.data_ptr(), dt, steps_done)
+        g = buf.view(3, n, 3)
+        s1 = b1.view(3, n, 3)
+        dev = [float(((g[k] - s1[k]).abs().max() / s1[k].abs().max()).item()) for k in range(3)]
+        out["vs_single_rank"] = {"steps": int(steps_done), "pos": dev[0], "vel": dev[1], "acc": dev[2],
+                                 "ok": bool(dev[0] < 1e-5 and dev[1] < 1e-4),
+                                 "what": "max |sharded - single rank| / max |single rank| after the same steps (same particle order: the kd build is bit-exact whoever runs it)"}
+    return out
 
 
 def bench_direct(nb, torch, dist, local, peaks, rank, world, n=1 << 20):
@@ -436,28 +500,65 @@ def bench_fmm2d(nb, torch, local, n=1 << 22, order=5, steps=4):
             "gpu_launches": int(info.kernel_launches - l0), "cpu_baseline": cpu}
 
 
-def cpu_baseline(n, order, m2l_first, bounded, steps=None, warmup=0):
-    """reference CPU path (oracle/_ref) timed on the host cores; bounded sample of the workload"""
+def pick_ref_threads(order, cores, n_probe=1 << 20):
+    """CPU_THREADS sweep of SURVEY.md section 8(d): parasort's splitter scan is O(N x threads), so more threads is not
+    monotonically faster.  One steady-state leapfrog step per candidate at n_probe particles; returns (best, table)."""
+    from refs import Ref
+    cands = sorted({t for t in (8, 16, 32, cores) if 1 <= t <= max(cores, 8)})
+    st = Ref.init_ga(n_probe)
+    import coulomb_oscillators_b200 as nb
+    par = nb.default_param(n_probe)
+    table = {}
+    for t in cands:
+        ref = Ref(order=order, threads=t, unsort=0)
+        buf = np.zeros(9 * n_probe, np.float32)
+        buf[:6 * n_probe] = st.reshape(-1)
+        ref.eval(3, buf, n_probe, par)
+        ref.integrate(1, 3, buf, n_probe, par, 5e-4, 1)       # state now in tree order (steady state of a simulation)
+        t0 = time.perf_counter()
+        ref.integrate(1, 3, buf, n_probe, par, 5e-4, 2)
+        table[t] = (time.perf_counter() - t0) / 2
+    best = min(table, key=table.get)
+    return best, {str(k): round(v, 4) for k, v in table.items()}
+
+
+def cpu_baseline(n, order, m2l_first, bounded, steps=None, warmup=0, budget_s=150.0):
+    """The reference's own CPU path (oracle/_ref = the unmodified reference compiled where it lies, kind "reference"):
+    coulombOscillatorFMMKD3_cpu under leapfrog (main3.cu:65-69, integrator.cuh:68-96), initial conditions from the
+    reference's own initGA, CPU_THREADS = best of a sweep.  bounded = True (the cpu_baseline leg of our arm): a sample
+    of N = 2^22 particles, 3 steps.  bounded = False (--impl reference): the stated N; the number of timed steps is
+    cut only if the run would not end within budget_s seconds (the line then reports the steps actually timed)."""
     from refs import Ref, Oracle
     import coulomb_oscillators_b200 as nb
     cores = os.cpu_count() or 1
     if Ref.available():
-        ns = min(n, 1 << 21) if bounded else min(n, 1 << 22)
-        threads = min(cores, 64)
+        ns = min(n, 1 << 22) if bounded else n
+        threads, sweep = pick_ref_threads(order, cores)
         ref = Ref(order=order, threads=threads, unsort=0)
         buf = np.zeros(9 * ns, np.float32)
-        buf[:6 * ns] = nb.init_ga(ns).reshape(-1)
+        buf[:6 * ns] = Ref.init_ga(ns).reshape(-1)
         par = nb.default_param(ns)
-        ref.eval(3, buf, ns, par)                       # precompute accelerations (main3.cu:835-839)
-        for _ in range(warmup):
-            ref.integrate(1, 3, buf, ns, par, 5e-4, 1)
+        t0 = time.perf_counter()
+        ref.eval(3, buf, ns, par)                       # precompute accelerations (main3.cu:835-839); sorts the random input
+        t_first = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ref.integrate(1, 3, buf, ns, par, 5e-4, 1)      # first step: untimed warm-up (always), gives the step time
+        t_step = time.perf_counter() - t0
         k = steps or 3
+        w = max(warmup - 1, 0)
+        if (k + w) * t_step > budget_s:                 # keep the whole run within a few minutes
+            w = 0
+            k = max(3, min(k, int(budget_s / t_step)))
+        if w:
+            ref.integrate(1, 3, buf, ns, par, 5e-4, w)
         t0 = time.perf_counter()
         ref.integrate(1, 3, buf, ns, par, 5e-4, k)
         t = time.perf_counter() - t0
-        return {"value": ns * k / t, "unit": "particle-steps/s", "cores": threads, "kind": "reference",
-                "sample": f"{k} leapfrog steps of coulombOscillatorFMMKD3_cpu at N={ns} (p={order}, CPU_THREADS={threads}, "
-                          f"state already in tree order), {t:.1f} s", "ms_per_step": 1e3 * t / k}
+        return {"value": ns * k / t, "unit": "particle-steps/s", "cores": threads, "kind": "reference", "n": ns, "steps": k,
+                "host_cores": cores, "threads_sweep_s_per_step_at_2^20": sweep,
+                "sample": f"{k} leapfrog steps of coulombOscillatorFMMKD3_cpu at N={ns} (p={order}, CPU_THREADS={threads} = best of the sweep, "
+                          f"reference initGA ICs, state in tree order after {w + 1} warm-up step(s)), {t:.1f} s; first evaluation {t_first:.1f} s",
+                "ms_per_step": 1e3 * t / k}
     ns = min(n, 1 << 18)
     orc = Oracle(order=order, unsort=0, m2l_first=m2l_first, tree_steps=1)
     buf = np.zeros(9 * ns, np.float32)
@@ -468,8 +569,66 @@ def cpu_baseline(n, order, m2l_first, bounded, steps=None, warmup=0):
     t0 = time.perf_counter()
     orc.integrate(1, 3, buf, ns, par, 5e-4, k)
     t = time.perf_counter() - t0
-    return {"value": ns * k / t, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+    return {"value": ns * k / t, "unit": "particle-steps/s", "cores": 1, "kind": "port", "n": ns, "steps": k,
             "sample": f"{k} leapfrog steps of the C restatement at N={ns}, {t:.1f} s", "ms_per_step": 1e3 * t / k}
+
+
+def reference_gpu_baseline(local, n=1 << 20, steps=16, timeout=240):
+    """Second stated baseline ("the same generic source compiled with -arch=sm_100"): the
+    reference's own GPU path, coulombOscillatorFMMKD3 under its leapfrog, timed in a separate process
+    (tools/ref_gpu_baseline.py: a crash or a time-out of the reference cannot take the bench down)."""
+    try:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")   # the reference hard-wires device 0 (fmm_cart3_kdtree.cuh:1529): remap
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=vis.split(",")[local] if vis else str(local))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_gpu_baseline.py"), str(n), str(steps)],
+                           capture_output=True, text=True, timeout=timeout, env=env)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"unavailable": f"rc={r.returncode}: {(r.stderr or r.stdout).strip()[-200:]}"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
+
+
+def config1_direct_leg(nb, torch, local, n=8192, steps=100):
+    """BASELINE config 1: N = 8192 direct sum, leapfrog, 100 steps.  Reference: leapfrog(coulombOscillatorDirect_cpu, ...,
+    step_cpu) on the host cores (oracle/_ref); ours: nbco_integrate(LEAPFROG, COULOMB_DIRECT3) on the device."""
+    out = {"n": n, "steps": steps}
+    st = nb.init_ga(n)
+    par = nb.default_param(n)
+    ctx = nb.Context(device=local)
+    buf = torch.zeros(9 * n, dtype=torch.float32, device="cuda")
+    buf[:6 * n] = torch.from_numpy(st.reshape(-1)).cuda()
+    dpar = torch.from_numpy(par).cuda()
+    ev = nb.EVAL_COULOMB_DIRECT3
+    ctx.compute_force(ev, buf.data_ptr(), n, dpar.data_ptr())
+    ctx.integrate(nb.LEAPFROG, ev, buf.data_ptr(), n, dpar.data_ptr(), 5e-4, 5)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    ctx.integrate(nb.LEAPFROG, ev, buf.data_ptr(), n, dpar.data_ptr(), 5e-4, steps)
+    e1.record(stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    out["ours"] = {"ms": ms, "Ginteractions_per_s": n * n * steps / (ms * 1e-3) / 1e9, "particle_steps_per_s": n * steps / (ms * 1e-3)}
+    try:
+        from refs import Ref
+        if Ref.available():
+            threads = min(os.cpu_count() or 1, 64)
+            ref = Ref(order=3, threads=threads)
+            b = np.zeros(9 * n, np.float32)
+            b[:6 * n] = st.reshape(-1)
+            ref.eval(2, b, n, par)
+            t0 = time.perf_counter()
+            ref.integrate(1, 2, b, n, par, 5e-4, steps)
+            t = time.perf_counter() - t0
+            out["reference_cpu"] = {"s": t, "cores": threads, "Ginteractions_per_s": n * n * steps / t / 1e9,
+                                    "particle_steps_per_s": n * steps / t, "kind": "reference",
+                                    "what": "leapfrog(coulombOscillatorDirect_cpu, ..., step_cpu, 1) x 100 (main3.cu:53-57, integrator.cuh:68-96)"}
+    except Exception as e:  # noqa: BLE001
+        out["reference_cpu"] = {"error": str(e)[:200]}
+    return out
 
 
 def run_reference(args):
@@ -480,11 +639,11 @@ def run_reference(args):
     cpu = cpu_baseline(args.n, args.order, args.m2l_first, bounded=False, steps=args.steps, warmup=args.warmup)
     out = {
         "impl": "reference", "metric": "3D FMM particle-steps/s", "value": cpu["value"], "unit": "particle-steps/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"3D kd-tree FMM leapfrog, N={args.n}, p={args.order}, r=1, reference initGA ICs "
-                               f"(reference CPU path timed on a bounded sample, see cpu_baseline.sample)",
-                   "n": args.n, "order": args.order},
+        "n_gpus": world, "steps": cpu["steps"], "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"3D kd-tree FMM leapfrog, N={cpu['n']}, p={args.order}, r=1, reference initGA ICs; the reference's own "
+                               f"CPU path (coulombOscillatorFMMKD3_cpu, rebuilds the tree every evaluation) on the host cores",
+                   "n": cpu["n"], "order": args.order, "same_n_as_requested": bool(cpu["n"] == args.n)},
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -503,6 +662,7 @@ def main():
     ap.add_argument("--m2l-first", dest="m2l_first", type=int, default=1)
     ap.add_argument("--no-direct", dest="direct", action="store_false")
     ap.add_argument("--no-fmm2d", dest="fmm2d", action="store_false")
+    ap.add_argument("--no-ref-gpu", dest="ref_gpu", action="store_false", help="skip the reference-GPU-path baseline (separate process)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

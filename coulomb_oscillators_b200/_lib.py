@@ -4,7 +4,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libnbco.so")
+# NBCO_LIB: an alternative build of the SAME C ABI (tools/ab_phases.py times an older build beside the current one)
+lib_path = os.environ.get("NBCO_LIB") or os.path.join(_HERE, "libnbco.so")
 
 EVAL_DIRECT3, EVAL_FMM3_KD, EVAL_COULOMB_DIRECT3, EVAL_COULOMB_FMM3_KD = 0, 1, 2, 3
 EVAL_DIRECT2, EVAL_FMM2, EVAL_COULOMB_DIRECT2, EVAL_COULOMB_FMM2 = 4, 5, 6, 7

@@ -145,8 +145,12 @@ static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64
 	for (int64_t s = 0; s < nsteps; ++s)
 	{
 		NBCO_TRY(kick_drift_launch(ctx, pos + 3*lo, vel + 3*lo, acc + 3*lo, h, h, s > 0, dtf, hi - lo));
+		// only the own range moved: the other ranges of this rank's arrays are stale from here on (a rebuild must
+		// fetch them from their owners, even right after nbco_peer_gather)
+		if (ctx->peer.active) ctx->peer.have_full = false;
 		NBCO_TRY(eval_dispatch(ctx, evaluator, pos, acc, n, param));
 	}
+	if (ctx->peer.active) ctx->peer.have_full = false;
 	return step_launch(ctx, vel + 3*lo, acc + 3*lo, h, hi - lo);
 }
 
@@ -206,7 +210,7 @@ void nbco_destroy(nbco_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->cfg.device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	peer_release(ctx);
+	peer_release(ctx, true);
 	fmm3_destroy(ctx);
 	fmm2_destroy(ctx);
 	ctx->pos4.release(); ctx->red.release(); ctx->h_state.release(); ctx->h_param.release();
@@ -283,6 +287,7 @@ int nbco_step(nbco_ctx *ctx, void *d_b, const void *d_a, float ds, int64_t n)
 {
 	ENTER(ctx);
 	NBCO_TRY(step_launch(ctx, (float *)d_b, (const float *)d_a, ds, n));
+	ctx->peer.have_full = false; // peer mode: the caller advances (part of) the state behind the evaluator's back
 	return sync(ctx);
 }
 

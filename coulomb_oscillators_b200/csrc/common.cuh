@@ -104,7 +104,8 @@ bool fmm3_next_rebuilds(nbco_ctx *ctx, int64_t n); // will the next FMM evaluati
 int peer_barrier(nbco_ctx *ctx);                                           // all ranks, on the context streams
 int peer_publish(nbco_ctx *ctx, const float *d_full, int which, int64_t n);  // own range of pos (0) / vel (1) -> published mirror
 int peer_pull(nbco_ctx *ctx, float *d_full, int which, int64_t n);           // the other ranks' ranges <- their mirrors
-void peer_release(nbco_ctx *ctx);
+void peer_release(nbco_ctx *ctx, bool free_exports);
+int peer_report_error(nbco_ctx *ctx, unsigned *h_err); // reads and clears the sticky barrier time-out word
 int fmm3_peer_buffers(nbco_ctx *ctx, int64_t n, void **center, void **mpole); // fmm3.cu: plans, returns the node arrays
 // fmm2.cu (2D fp64 path)
 int fmm2_launch(nbco_ctx *ctx, double *d_pos, double *d_acc, int64_t n, const double *d_param, bool fuse_elastic);

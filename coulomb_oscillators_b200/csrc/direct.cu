@@ -18,6 +18,7 @@
 // Multi-GPU: targets are sharded by rank (nbco_shard_range), sources are the full set.
 
 #include "common.cuh"
+#include <cmath>
 
 namespace nbco {
 
@@ -179,9 +180,15 @@ direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 	}
 	const f32x2 eps2p = pack2(eps2, eps2);
 
-	for (int64_t base = 0; base < n_src; base += kTileJ)
+	// split-j: blockIdx.y takes the y-th of gridDim.y equal runs of source tiles (fills the last wave of the grid when
+	// the target blocks alone do not divide the SM slots; partial sums are then combined with atomicAdd)
+	const int64_t tiles = (n_src + kTileJ - 1) / kTileJ;
+	const int64_t j_lo = (tiles * blockIdx.y / gridDim.y) * kTileJ;
+	const int64_t j_hi_ = (tiles * (blockIdx.y + 1) / gridDim.y) * kTileJ;
+	const int64_t j_hi = j_hi_ < n_src ? j_hi_ : n_src;
+	for (int64_t base = j_lo; base < j_hi; base += kTileJ)
 	{
-		int cnt = (int)((n_src - base < kTileJ) ? (n_src - base) : kTileJ);
+		int cnt = (int)((j_hi - base < kTileJ) ? (j_hi - base) : kTileJ);
 		__syncthreads();
 		for (int j = tid; j < cnt; j += BLOCK)
 		{
@@ -233,9 +240,18 @@ direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 		int64_t i = i0 + (int64_t)k * BLOCK;
 		if (i < i_end)
 		{
-			acc[3*i]   = scale * sum[k].sx;
-			acc[3*i+1] = scale * sum[k].sy;
-			acc[3*i+2] = scale * sum[k].sz;
+			if (gridDim.y == 1)
+			{
+				acc[3*i]   = scale * sum[k].sx;
+				acc[3*i+1] = scale * sum[k].sy;
+				acc[3*i+2] = scale * sum[k].sz;
+			}
+			else
+			{
+				atomicAdd(acc + 3*i, scale * sum[k].sx);
+				atomicAdd(acc + 3*i + 1, scale * sum[k].sy);
+				atomicAdd(acc + 3*i + 2, scale * sum[k].sz);
+			}
 		}
 	}
 }
@@ -334,7 +350,27 @@ int direct3_launch(nbco_ctx *ctx, const float *d_pos, float *d_acc, int64_t n, c
 		case 11: LAUNCH_P(2, 256, 8)
 		case 12: LAUNCH_P(4, 128, 8)
 		case 13: LAUNCH(direct3_packed_kernel, 4); break;
-		default: LAUNCH_P(4, 256, 4) // measured fastest on B200 (profiles/r01_notes.md)
+		default: // <4, 256, 4>: measured fastest on B200 (profiles/r01_notes.md)
+		{
+			// grid: target blocks x source parts.  The target blocks alone leave the last wave partly empty (N = 2^20:
+			// 1024 blocks on 148 x occ slots; a rank of 8: 128 blocks on 148 SMs = 86 % of the chip), so the source
+			// range is cut into `parts` runs such that blocks x parts fills whole waves.
+			static int occ = 0;
+			if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, direct3_packed_kernel<4, 256, 4>, 256, 0) != cudaSuccess || occ < 1)) occ = 1;
+			const int64_t bx = (cnt + 256 * 4 - 1) / (256 * 4), slots = (int64_t)ctx->sm_count * occ;
+			const int64_t tiles = (n + kTileJ - 1) / kTileJ;
+			int parts = 1;
+			double best = 0.0;
+			for (int sp = 1; sp <= 160 && sp * 8 <= tiles; ++sp)
+			{
+				const double waves = (double)(bx * sp) / (double)slots, eff = waves / std::ceil(waves);
+				if (eff > best + 0.01) { best = eff; parts = sp; }
+				if (best > 0.97) break;
+			}
+			if (parts > 1) NBCO_CUDA(cudaMemsetAsync(d_acc + 3 * ib, 0, 12 * (size_t)cnt, ctx->stream));
+			direct3_packed_kernel<4, 256, 4><<<dim3((unsigned)bx, (unsigned)parts), 256, 0, ctx->stream>>>(src, n, ib, ie, d_acc, d_param, eps2);
+			break;
+		}
 #undef LAUNCH_P
 	}
 #undef LAUNCH

@@ -1122,7 +1122,7 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 	return NBCO_ERR_OVERFLOW;
 }
 
-extern const OrderOps kOrderOps1, kOrderOps2, kOrderOps3, kOrderOps4, kOrderOps5, kOrderOps6;
+extern const OrderOps kOrderOps1, kOrderOps2, kOrderOps3, kOrderOps4, kOrderOps5, kOrderOps6, kOrderOps7, kOrderOps8, kOrderOps9, kOrderOps10;
 
 const OrderOps *order_ops(int order)
 {
@@ -1134,6 +1134,10 @@ const OrderOps *order_ops(int order)
 		case 4: return &kOrderOps4;
 		case 5: return &kOrderOps5;
 		case 6: return &kOrderOps6;
+		case 7: return &kOrderOps7;
+		case 8: return &kOrderOps8;
+		case 9: return &kOrderOps9;
+		case 10: return &kOrderOps10;
 		default: return nullptr;
 	}
 }

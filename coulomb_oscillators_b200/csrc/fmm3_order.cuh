@@ -208,18 +208,20 @@ m2l_kernel(TreeData t, const int2 *__restrict__ list, const u32 *__restrict__ co
 		if (flags & 1)
 		{
 			load_tuple<sym_off(P)>(M, node_mpole(t, np.y));
+			m2l_weight<P>(M);
 #pragma unroll
 			for (int k = 0; k < pad4<trl_off(P + 1)>(); ++k) Lq[k] = 0.f;
-			m2l_acc<P>(Lq, M, dx, dy, dz, rinv);
+			m2l_acc_w<P>(Lq, M, dx, dy, dz, rinv);
 			atomic_add_tuple<trl_off(P + 1)>(t.local + (int64_t)np.x * t.sL, Lq); // slot 0 receives +0
 		}
 		// target np.y, source np.x
 		if (flags & 2)
 		{
 			load_tuple<sym_off(P)>(M, node_mpole(t, np.x));
+			m2l_weight<P>(M);
 #pragma unroll
 			for (int k = 0; k < pad4<trl_off(P + 1)>(); ++k) Lq[k] = 0.f;
-			m2l_acc<P>(Lq, M, -dx, -dy, -dz, rinv);
+			m2l_acc_w<P>(Lq, M, -dx, -dy, -dz, rinv);
 			atomic_add_tuple<trl_off(P + 1)>(t.local + (int64_t)np.y * t.sL, Lq); // slot 0 receives +0
 		}
 	}

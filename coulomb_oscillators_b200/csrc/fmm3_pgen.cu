@@ -391,5 +391,16 @@ NBCO_GENERIC_ORDER(5)
 #if NBCO_STATIC_ORDER_MAX < 6
 NBCO_GENERIC_ORDER(6)
 #endif
+// orders 7..NBCO_MAX_ORDER always run the generic loops (the reference switches to its runtime m2l_acc3 /
+// *_kdtree2 kernels from p = 7 too, fmm_cart3_kdtree.cuh:376-381,673-704); `nbco3 -test` sweeps p = 1..10 like main3.cu:790-811
+#if NBCO_STATIC_ORDER_MAX < 7
+NBCO_GENERIC_ORDER(7)
+#endif
+#if NBCO_STATIC_ORDER_MAX < 8
+NBCO_GENERIC_ORDER(8)
+#endif
+NBCO_GENERIC_ORDER(9)
+NBCO_GENERIC_ORDER(10)
+static_assert(NBCO_MAX_ORDER == 10, "instantiate the generic orders up to NBCO_MAX_ORDER");
 
 } // namespace nbco

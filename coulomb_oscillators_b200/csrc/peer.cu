@@ -21,7 +21,7 @@ struct BarrierArgs { unsigned long long *flags[kPeerMax]; int world, me; };
 
 // every rank writes `epoch` into slot [me] of every rank's flag array, then waits until all slots of its own
 // array reached `epoch`.  Bounded spin: a rank that never arrives raises err instead of hanging the GPU.
-__global__ void peer_barrier_kernel(BarrierArgs a, unsigned long long epoch, unsigned *err)
+__global__ void peer_barrier_kernel(BarrierArgs a, unsigned long long epoch, unsigned *err, long long timeout_cycles)
 {
 	const int q = threadIdx.x;
 	__threadfence_system();
@@ -37,7 +37,7 @@ __global__ void peer_barrier_kernel(BarrierArgs a, unsigned long long epoch, uns
 		const long long t0 = clock64();
 		while (*src < epoch)
 		{
-			if (clock64() - t0 > 8000000000ll) { *err = 1u; break; } // ~4 s at 2 GHz
+			if (clock64() - t0 > timeout_cycles) { *err = 1u; break; }
 			__nanosleep(100);
 		}
 	}
@@ -54,7 +54,18 @@ int peer_barrier(nbco_ctx *ctx)
 	for (int q = 0; q < kPeerMax; ++q) a.flags[q] = q < ps.world ? (unsigned long long *)ps.pubp[q] : nullptr;
 	a.world = ps.world; a.me = ps.me;
 	unsigned *err = (unsigned *)((char *)ps.pub.p + 512);
-	peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(a, ++ps.epoch, err);
+	// Bounded spin.  Ranks may arrive with host-side skew (a snapshot written by one rank, first-call allocations, a GC
+	// pause in a Python driver): the default bound is generous (30 s of SM clock at ~2 GHz); NBCO_PEER_TIMEOUT_S overrides.
+	// Callers that do rank-local host work between two library calls should meet at a host barrier before re-entering.
+	static long long timeout_cycles = 0;
+	if (!timeout_cycles)
+	{
+		const char *e = getenv("NBCO_PEER_TIMEOUT_S");
+		double sec = e ? atof(e) : 30.0;
+		if (!(sec > 0.0)) sec = 30.0;
+		timeout_cycles = (long long)(sec * 2.0e9);
+	}
+	peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(a, ++ps.epoch, err, timeout_cycles);
 	++ctx->launches;
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;
@@ -84,7 +95,10 @@ int peer_pull(nbco_ctx *ctx, float *d_full, int which, int64_t n)
 	return NBCO_OK;
 }
 
-void peer_release(nbco_ctx *ctx)
+// CUDA IPC: every importer must close its mapping before the exporter frees the allocation.  Detaching therefore only
+// CLOSES this rank's imports; the exported buffers (pub here, centres / multipoles in the FMM plan) stay allocated until
+// nbco_destroy, and callers put a host barrier between nbco_peer_detach and nbco_destroy.
+void peer_release(nbco_ctx *ctx, bool free_exports)
 {
 	PeerState &ps = ctx->peer;
 	for (int q = 0; q < kPeerMax; ++q)
@@ -93,8 +107,21 @@ void peer_release(nbco_ctx *ctx)
 			cudaIpcCloseMemHandle(ps.center[q]); cudaIpcCloseMemHandle(ps.mpole[q]); cudaIpcCloseMemHandle(ps.pubp[q]);
 			ps.opened[q] = false;
 		}
-	ps.pub.release();
+	if (free_exports) ps.pub.release();
 	ps.active = false;
+}
+
+int peer_report_error(nbco_ctx *ctx, unsigned *h_err)
+// reads and CLEARS the sticky time-out word of this rank's flag block (the context stays usable after a detach/export cycle)
+{
+	*h_err = 0;
+	PeerState &ps = ctx->peer;
+	if (!ps.pub.p) return NBCO_OK;
+	unsigned *d = (unsigned *)((char *)ps.pub.p + 512);
+	NBCO_CUDA(cudaMemcpyAsync(h_err, d, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (*h_err) NBCO_CUDA(cudaMemsetAsync(d, 0, 4, ctx->stream));
+	return NBCO_OK;
 }
 
 } // namespace nbco
@@ -181,8 +208,10 @@ int nbco_peer_detach(nbco_ctx *ctx)
 	if (!ctx) { set_error("null context"); return NBCO_ERR_INVALID; }
 	NBCO_CUDA(cudaSetDevice(ctx->cfg.device));
 	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
-	peer_release(ctx);
+	peer_release(ctx, false);
+	DevBuf keep = ctx->peer.pub; // still mapped by the other ranks until they detach too: freed at nbco_destroy
 	ctx->peer = PeerState();
+	ctx->peer.pub = keep;
 	return NBCO_OK;
 }
 
@@ -191,9 +220,8 @@ int nbco_peer_barrier(nbco_ctx *ctx)
 	if (!ctx) { set_error("null context"); return NBCO_ERR_INVALID; }
 	NBCO_CUDA(cudaSetDevice(ctx->cfg.device));
 	NBCO_TRY(peer_barrier(ctx));
-	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
 	unsigned err = 0;
-	if (ctx->peer.active) NBCO_CUDA(cudaMemcpy(&err, (char *)ctx->peer.pub.p + 512, 4, cudaMemcpyDeviceToHost));
+	NBCO_TRY(peer_report_error(ctx, &err));
 	if (err) { set_error("peer barrier timed out (a rank did not arrive)"); return NBCO_ERR_CUDA; }
 	return NBCO_OK;
 }

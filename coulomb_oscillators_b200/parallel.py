@@ -20,6 +20,11 @@ def all_gather_shards(local_shard, n, group=None):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     sizes = shard_sizes(n, world)
+    if len(set(sizes)) == 1:
+        # equal shards (n divisible by the world size): one collective straight into the result, no padding / cat passes
+        out = torch.empty((n, 3), dtype=local_shard.dtype, device=local_shard.device)
+        dist.all_gather_into_tensor(out, local_shard.contiguous(), group=group)
+        return out
     pad = max(sizes)
     buf = torch.zeros((pad, 3), dtype=local_shard.dtype, device=local_shard.device)
     buf[: local_shard.shape[0]] = local_shard

@@ -66,7 +66,7 @@ typedef struct nbco_config
 	                          0 = use (double)eps2 */
 } nbco_config;
 
-#define NBCO_MAX_ORDER 6    /* 3D kd-tree FMM */
+#define NBCO_MAX_ORDER 10   /* 3D kd-tree FMM: 1..6 unrolled templates, 7..10 runtime-order loops (main3.cu:790-811 sweeps 1..10) */
 #define NBCO2_MAX_ORDER 10  /* 2D FMM (the reference's -test loop runs p = 1..10, main.cu:844) */
 
 void nbco_default_config(nbco_config *cfg);

@@ -268,4 +268,47 @@ double ref_direct3_gpu_seconds(const float *pos, float *acc, int n, const float 
 	return s;
 }
 
+// ---- reference GPU kd-tree FMM under its own leapfrog (main3.cu:59-63,841-846; generic SIMT source compiled for
+// sm_100): the second stated baseline of bench.py.  buf = [pos | vel | acc] on the host (9 n floats), read back at
+// the end (tree order, like the reference's own snapshots).  Returns seconds per step or < 0 on a CUDA error. ----
+double ref_fmm3_gpu_step_seconds(float *buf, int n, const float *param6, double dt, int warm, int steps)
+{
+	SCAL *d_buf, *d_par;
+	if (cudaMalloc(&d_buf, sizeof(VEC)*3*(size_t)n) != cudaSuccess) return -1;
+	if (cudaMalloc(&d_par, sizeof(SCAL)*6) != cudaSuccess) return -1;
+	cudaMemcpy(d_buf, buf, sizeof(VEC)*2*(size_t)n, cudaMemcpyHostToDevice);
+	cudaMemcpy(d_par, param6, sizeof(SCAL)*6, cudaMemcpyHostToDevice);
+	SCAL dts = (SCAL)dt;
+	compute_force(coulombOscillatorFMMKD3, d_buf, n, d_par); // main3.cu:835-839
+	for (int s = 0; s < warm; ++s)
+		leapfrog(coulombOscillatorFMMKD3, d_buf, n, d_par, dts, step, 1);
+	if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+	auto t0 = steady_clock::now();
+	for (int s = 0; s < steps; ++s)
+		leapfrog(coulombOscillatorFMMKD3, d_buf, n, d_par, dts, step, 1);
+	if (cudaDeviceSynchronize() != cudaSuccess) return -3;
+	double sec = duration_cast<microseconds>(steady_clock::now() - t0).count() * 1e-6 / (steps > 0 ? steps : 1);
+	cudaMemcpy(buf, d_buf, sizeof(VEC)*3*(size_t)n, cudaMemcpyDeviceToHost);
+	cudaFree(d_buf); cudaFree(d_par);
+	return sec;
+}
+
+// one evaluation of a reference GPU evaluator on host data (0 direct3, 1 fmm_cart3_kdtree with the current globals);
+// pos (and vel behind it, when b_unsort is false) come back as the evaluator left them
+int ref_eval_gpu(int which, float *buf, int n, const float *param6)
+{
+	SCAL *d_buf, *d_par;
+	if (cudaMalloc(&d_buf, sizeof(VEC)*3*(size_t)n) != cudaSuccess) return -1;
+	if (cudaMalloc(&d_par, sizeof(SCAL)*6) != cudaSuccess) return -1;
+	cudaMemcpy(d_buf, buf, sizeof(VEC)*2*(size_t)n, cudaMemcpyHostToDevice);
+	cudaMemcpy(d_par, param6, sizeof(SCAL)*6, cudaMemcpyHostToDevice);
+	if (which == 0) compute_force(direct3, d_buf, n, d_par);
+	else if (which == 1) compute_force(fmm_cart3_kdtree, d_buf, n, d_par);
+	else return -4;
+	if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+	cudaMemcpy(buf, d_buf, sizeof(VEC)*3*(size_t)n, cudaMemcpyDeviceToHost);
+	cudaFree(d_buf); cudaFree(d_par);
+	return 0;
+}
+
 } // extern "C"

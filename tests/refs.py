@@ -140,6 +140,10 @@ class Ref:
             L.ref_fmm3_phases.argtypes = [_f, _f, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_void_p, C.c_void_p, C.c_longlong, _l]
             L.ref_direct3_gpu_seconds.restype = C.c_double
             L.ref_direct3_gpu_seconds.argtypes = [_f, _f, C.c_int, _f, C.c_int]
+            if hasattr(L, "ref_fmm3_gpu_step_seconds"):   # harness of round 2 (reference GPU path as a second baseline)
+                L.ref_fmm3_gpu_step_seconds.restype = C.c_double
+                L.ref_fmm3_gpu_step_seconds.argtypes = [_f, C.c_int, _f, C.c_double, C.c_int, C.c_int]
+                L.ref_eval_gpu.argtypes = [C.c_int, _f, C.c_int, _f]
             cls._lib = L
         return cls._lib
 
@@ -151,6 +155,15 @@ class Ref:
 
     def apply(self):
         self.L.ref_config(*self.cfg)
+
+    @classmethod
+    def init_ga(cls, n, sigma_x=(0.003, 0.001, 0.01), omega0=(1.095, 1.0, 1.0)):
+        """the reference's own initGA (main3.cu:114-137,662-664) -> (2, n, 3) float32 [pos, vel]"""
+        x3 = np.asarray(sigma_x, np.float32)
+        u3 = (np.asarray(omega0, np.float32) * x3).astype(np.float32)   # main3.cu:241-245
+        buf = np.zeros(6 * n, np.float32)
+        cls.lib().ref_init_ga(buf, n, x3, u3)
+        return buf.reshape(2, n, 3)
 
     def eval(self, which, buf, n, param=None):
         self.apply()
@@ -199,13 +212,20 @@ class Ref:
 
 def unique_axes(pos):
     """make every coordinate of every axis distinct (bump duplicates by one ulp until strictly
-    increasing): on such inputs the reference's unstable sorts have a unique answer"""
+    increasing): on such inputs the reference's unstable sorts have a unique answer.
+    Vectorised: in the monotone integer image k of the floats the rule v[i] = max(v[i], v[i-1] + 1 ulp) is
+    k'[i] = max(k[i], k'[i-1] + 1), i.e. k' - i = running maximum of k - i (usable at N = 2^24)."""
     pos = np.array(pos, np.float32, copy=True)
     for k in range(3):
         o = np.argsort(pos[:, k], kind="stable")
         v = pos[o, k].copy()
-        for i in range(1, len(v)):
-            if v[i] <= v[i - 1]:
-                v[i] = np.nextafter(v[i - 1], np.float32(np.inf))
+        v[v == 0] = 0.0                                      # -0.0 and +0.0 are one value
+        b = v.view(np.int32).astype(np.int64)
+        key = np.where(b >= 0, b, -(b & 0x7FFFFFFF))          # monotone in the float value, one step per ulp
+        i = np.arange(len(v), dtype=np.int64)
+        key = np.maximum.accumulate(key - i) + i
+        nb_ = np.where(key >= 0, key, (-key) | 0x80000000).astype(np.uint32)
+        v = nb_.view(np.float32)
+        assert np.all(np.diff(v) > 0)
         pos[o, k] = v
     return pos

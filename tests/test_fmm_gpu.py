@@ -50,6 +50,8 @@ def check_against_oracle(pos0, vel0, par, order, m2l_first, tol_max=None, **cfg)
     (8, 3, 1, "ga"), (9, 1, 0, "ga"), (100, 3, 1, "ga"), (1000, 2, 0, "ga"), (8192, 3, 0, "ga"), (8192, 3, 1, "ga"),
     (8193, 3, 1, "ga"), (20011, 1, 1, "ga"), (30000, 4, 0, "cube"), (65536, 5, 1, "cube"), (50000, 6, 0, "ga"),
     (100003, 3, 1, "ga"), (1 << 18, 3, 1, "cube"),
+    # orders 7..10 run the runtime-order kernels (fmm3_pgen.cu), like the reference's *_kdtree2 / m2l_acc3 path
+    (20000, 7, 1, "ga"), (30000, 8, 0, "cube"), (12000, 9, 1, "ga"), (20000, 10, 0, "ga"),
 ])
 def test_fmm_matches_oracle(n, order, m2l_first, dist):
     st = nb.init_ga(n) if dist == "ga" else nb.init_test_cube(n)
@@ -114,6 +116,32 @@ def test_fmm_matches_live_reference(n, order):
     assert np.array_equal(P, R["p2p"]) and np.array_equal(M, R["m2l"])
     m, mx = mean_rel_err(acc, R["acc_sorted"])
     assert m < TOL_MEAN and mx < (TOL_MAX if n <= (1 << 16) else 3e-5), (m, mx)
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not shipped")
+def test_fmm_headline_size_matches_live_reference():
+    """N = 2^24, p = 3 -- the configuration bench.py quotes -- against the unmodified reference run live on the host
+    cores (one evaluation of its CPU phase functions, traversal in the GPU kernel's test order m2l_first = 1):
+    permutation, boxes, split axes, centres and BOTH interaction lists bit-exact on tie-free coordinates, forces
+    within the tolerance written here."""
+    n = 1 << 24
+    st = nb.init_ga(n)
+    st[0] = unique_axes(st[0])
+    par = nb.default_param(n)
+    R = Ref(order=3, threads=os.cpu_count()).fmm3_phases(st[0], par, 1)
+    assert R["levels"] == 21
+    ctx = nb.Context(order=3, unsort=0, m2l_first=1)
+    pos, vel = st[0].copy(), st[1].copy()
+    acc = ctx.eval_host(nb.EVAL_FMM3_KD, pos, vel, par)
+    T = ctx.fmm_tree()
+    for k in EXACT:
+        assert np.array_equal(T[k], R[k]), k
+    assert np.array_equal(pos, R["pos_sorted"])
+    P, M = ctx.fmm_lists()
+    assert len(P) > 300000 and len(M) > 3000000          # SURVEY.md section 6: P = 339 477, M = 3 185 098 (GPU order)
+    assert np.array_equal(P, R["p2p"]) and np.array_equal(M, R["m2l"])
+    m, mx = mean_rel_err(acc, R["acc_sorted"])
+    assert m < TOL_MEAN and mx < 3e-5, (m, mx)
 
 
 def test_fmm_equal_keys_follow_the_stable_sort_rule():
