@@ -225,16 +225,21 @@ def run_ours(args):
         dist.barrier()
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region, every step ----
+    # One GPU: nbco_run_host, the reference's resume-from-snapshot flow (main3.cu:629-658,835-858): the host holds the
+    # state [pos | vel] (the reference's state file), every step uploads it from pinned memory, recomputes a = f(x),
+    # takes one leapfrog step and reads [pos | vel] back: 24 N bytes each way and TWO force evaluations per step.
+    # (Round 1 moved [pos | vel | acc], 36 N each way, with one evaluation: PCIe-bound at 22.8 ms per step.)
     hbuf = torch.empty(9 * n, dtype=torch.float32).pin_memory()
     hbuf.copy_(buf.cpu())
     hnp = hbuf.numpy()
+    hpv = hnp[:6 * n].reshape(2, n, 3)
     ctx_e = nb.Context(device=local, order=order, unsort=0, tree_steps=8, m2l_first=args.m2l_first) if world == 1 else ctx
     e2e_steps = max(3, min(args.steps, 8))
     lo, hi = nb.shard_range(n, rank, world)
 
     def e2e_step():
         if world == 1:
-            ctx_e.step_host(nb.LEAPFROG, ev, hnp, n, par, dt, 1)
+            ctx_e.run_host(nb.LEAPFROG, ev, hpv, par, dt, 1)
         else:
             # every rank owns a tree-order range: it uploads its range of pos / vel / acc, the ranks step together
             # (remote data moves between the GPUs inside the evaluator), every rank reads its range back
@@ -320,11 +325,14 @@ def run_ours(args):
                    "n": n, "order": order, "levels": int(info.levels), "p2p_pairs": int(info.p2p_pairs),
                    "m2l_pairs": int(info.m2l_pairs), "m2l_first": args.m2l_first,
                    "l2_hygiene": "inputs larger than L2 (state 36 B x N + tree slab)" if 36 * n > 126e6 else "working set may fit L2",
-                   "e2e_copies": "every step: H2D [pos|vel|acc] from pinned memory + D2H of the same"},
+                   "e2e_copies": "every step: H2D [pos|vel] from pinned memory, a = f(x) recomputed on the device, one step, D2H [pos|vel]"},
         "roofline": roofline, "phases": phases, "cpu_baseline": cpu, "parity": parity,
         "rebuilds_per_step": round(rebuilds / max(evals, 1), 4), "reference_gpu_baseline": ref_gpu, "config1_direct_n8192": config1,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s",
-                "h2d_bytes_per_step": 36 * n, "d2h_bytes_per_step": 36 * n, "steps": e2e_steps},
+                "h2d_bytes_per_step": (24 if world == 1 else 36) * n, "d2h_bytes_per_step": (24 if world == 1 else 36) * n, "steps": e2e_steps,
+                "evaluations_per_step": 2 if world == 1 else 1,
+                "api": "nbco_run_host([pos|vel] in pinned host memory): upload, a = f(x), one leapfrog step, read back" if world == 1
+                       else "per rank: own range of [pos|vel|acc] host -> device, one peer-mode step, device -> host"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if direct is not None:

@@ -80,7 +80,7 @@ static int eval_dispatch(nbco_ctx *ctx, int evaluator, float *pos, float *acc, i
 static int sync(nbco_ctx *ctx)
 {
 	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
-	return NBCO_OK;
+	return fmm3_harvest(ctx, nullptr); // evaluations that were only enqueued: sticky overflow / barrier flags, phase timers
 }
 
 // One step of a scheme, enqueued on the context stream (no host synchronisation inside).
@@ -126,7 +126,8 @@ static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int
 
 // nsteps steps of a scheme.  Leapfrog runs fused: K(1/2) D | F | [K(1/2) K(1/2) D | F]* | K(1/2) -- the
 // same fma sequence per element as integrator.cuh:68-96 applied step by step, in fewer passes.
-static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64_t n, const float *param, float dtf, int64_t nsteps)
+static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64_t n, const float *param, float dtf, int64_t nsteps,
+                     cudaEvent_t ev_last_drift = nullptr)
 {
 	if (ctx->peer.active && scheme != NBCO_LEAPFROG) { set_error("peer mode integrates with the leapfrog scheme only"); return NBCO_ERR_INVALID; }
 	if (scheme != NBCO_LEAPFROG || nsteps <= 0)
@@ -145,6 +146,7 @@ static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64
 	for (int64_t s = 0; s < nsteps; ++s)
 	{
 		NBCO_TRY(kick_drift_launch(ctx, pos + 3*lo, vel + 3*lo, acc + 3*lo, h, h, s > 0, dtf, hi - lo));
+		if (ev_last_drift && s + 1 == nsteps) NBCO_CUDA(cudaEventRecord(ev_last_drift, ctx->stream));
 		// only the own range moved: the other ranges of this rank's arrays are stale from here on (a rebuild must
 		// fetch them from their owners, even right after nbco_peer_gather)
 		if (ctx->peer.active) ctx->peer.have_full = false;
@@ -213,7 +215,7 @@ void nbco_destroy(nbco_ctx *ctx)
 	peer_release(ctx, true);
 	fmm3_destroy(ctx);
 	fmm2_destroy(ctx);
-	ctx->pos4.release(); ctx->red.release(); ctx->h_state.release(); ctx->h_param.release();
+	ctx->pos4.release(); ctx->dpart.release(); ctx->red.release(); ctx->h_state.release(); ctx->h_param.release();
 	if (ctx->pinned) cudaFreeHost(ctx->pinned);
 	if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->ev_drift); cudaEventDestroy(ctx->ev_copied); }
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -369,20 +371,56 @@ int nbco_eval_host(nbco_ctx *ctx, int evaluator, float *h_pos, float *h_vel, flo
 	return sync(ctx);
 }
 
+static int ensure_copy_stream(nbco_ctx *ctx)
+{
+	if (ctx->copy_stream) return NBCO_OK;
+	NBCO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	NBCO_CUDA(cudaEventCreateWithFlags(&ctx->ev_drift, cudaEventDisableTiming));
+	NBCO_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+	return NBCO_OK;
+}
+
 int nbco_run_host(nbco_ctx *ctx, int scheme, int evaluator, float *h_pos_vel, float *h_acc, int64_t n,
                   const float *h_param, double dt, int64_t nsteps)
+// The reference's resume-from-snapshot flow (main3.cu:629-658,835-858) for a host-resident state: upload [pos | vel],
+// a = f(x), nsteps steps, read [pos | vel] back.  The copies overlap the force evaluations where the data flow allows:
+// the first evaluation needs the positions only, so the velocities are uploaded on a second stream meanwhile (unless
+// that evaluation rebuilds the tree and therefore permutes the velocities); after the last drift the positions are
+// final, so they are read back while the last evaluation runs (unless it permutes them).
 {
 	ENTER(ctx);
 	if (!h_pos_vel || n <= 0) { set_error("bad host buffers"); return NBCO_ERR_INVALID; }
 	float *d_buf, *d_param;
 	NBCO_TRY(stage(ctx, n, h_param, &d_buf, &d_param));
+	NBCO_TRY(ensure_copy_stream(ctx));
 	const size_t vb = sizeof(float) * 3 * (size_t)n;
-	NBCO_CUDA(cudaMemcpyAsync(d_buf, h_pos_vel, 2 * vb, cudaMemcpyHostToDevice, ctx->stream));
+	const bool fmm = evaluator == NBCO_EVAL_FMM3_KD || evaluator == NBCO_EVAL_COULOMB_FMM3_KD;
+	const bool peer = ctx->peer.active;
+	// uploads: positions on the compute stream, velocities on the copy stream
+	NBCO_CUDA(cudaEventRecord(ctx->ev_drift, ctx->stream));                 // d_buf is free (previous call finished on this stream)
+	NBCO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_drift, 0));
+	NBCO_CUDA(cudaMemcpyAsync(d_buf, h_pos_vel, vb, cudaMemcpyHostToDevice, ctx->stream));
+	NBCO_CUDA(cudaMemcpyAsync(d_buf + 3*n, h_pos_vel + 3*n, vb, cudaMemcpyHostToDevice, ctx->copy_stream));
+	NBCO_CUDA(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+	const bool first_permutes = fmm && (peer || fmm3_next_rebuilds(ctx, n));
+	if (first_permutes) NBCO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
 	NBCO_TRY(eval_dispatch(ctx, evaluator, d_buf, d_buf + 6*n, n, d_param)); // main3.cu:835-839
+	if (!first_permutes) NBCO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
 	const float dtf = (float)dt;
-	NBCO_TRY(run_steps(ctx, scheme, evaluator, d_buf, n, d_param, dtf, nsteps));
-	NBCO_CUDA(cudaMemcpyAsync(h_pos_vel, d_buf, 2 * vb, cudaMemcpyDeviceToHost, ctx->stream));
+	// will the LAST evaluation of the steps permute the state?  (evaluation index nsteps - 1 from here)
+	const bool early_pos = scheme == NBCO_LEAPFROG && nsteps >= 1 && !peer && (!fmm || !fmm3_rebuilds_in(ctx, n, nsteps - 1));
+	NBCO_TRY(run_steps(ctx, scheme, evaluator, d_buf, n, d_param, dtf, nsteps, early_pos ? ctx->ev_drift : nullptr));
+	if (early_pos)
+	{
+		NBCO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_drift, 0));
+		NBCO_CUDA(cudaMemcpyAsync(h_pos_vel, d_buf, vb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+		NBCO_CUDA(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+		NBCO_CUDA(cudaMemcpyAsync(h_pos_vel + 3*n, d_buf + 3*n, vb, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	else
+		NBCO_CUDA(cudaMemcpyAsync(h_pos_vel, d_buf, 2 * vb, cudaMemcpyDeviceToHost, ctx->stream));
 	if (h_acc) NBCO_CUDA(cudaMemcpyAsync(h_acc, d_buf + 6*n, vb, cudaMemcpyDeviceToHost, ctx->stream));
+	if (early_pos) NBCO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
 	return sync(ctx);
 }
 
@@ -402,12 +440,7 @@ int nbco_step_host(nbco_ctx *ctx, int scheme, int evaluator, float *h_buf, int64
 	const bool overlap = scheme == NBCO_LEAPFROG && nsteps == 1 && !ctx->peer.active && (!fmm || !fmm3_next_rebuilds(ctx, n));
 	if (overlap)
 	{
-		if (!ctx->copy_stream)
-		{
-			NBCO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-			NBCO_CUDA(cudaEventCreateWithFlags(&ctx->ev_drift, cudaEventDisableTiming));
-			NBCO_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
-		}
+		NBCO_TRY(ensure_copy_stream(ctx));
 		float *pos = d_buf, *vel = d_buf + 3*n, *acc = d_buf + 6*n;
 		const float h = (float)((long double)dtf * 0.5L);
 		NBCO_TRY(kick_drift_launch(ctx, pos, vel, acc, h, h, false, dtf, n));      // K(1/2) D, like run_steps

@@ -71,6 +71,7 @@ struct nbco_ctx
 
 	// direct sum scratch
 	nbco::DevBuf pos4;      // float4-padded copy of the sources
+	nbco::DevBuf dpart;     // partial sums of the source runs (direct sum, split over the sources)
 	// diagnostics scratch
 	nbco::DevBuf red;       // reduction partials
 	// host-call staging
@@ -99,7 +100,9 @@ int kinetic_elastic_launch(nbco_ctx *ctx, const float *d_buf, int64_t n, const f
 // fmm3.cu
 int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const float *d_param, bool fuse_elastic);
 void fmm3_destroy(nbco_ctx *ctx);
+int fmm3_harvest(nbco_ctx *ctx, int *overflow); // synchronisation point of the enqueued evaluations (counters, sticky flags, timers)
 bool fmm3_next_rebuilds(nbco_ctx *ctx, int64_t n); // will the next FMM evaluation of n particles permute pos / vel?
+bool fmm3_rebuilds_in(nbco_ctx *ctx, int64_t n, int64_t k); // ... and the one k evaluations after it?
 // peer.cu
 int peer_barrier(nbco_ctx *ctx);                                           // all ranks, on the context streams
 int peer_publish(nbco_ctx *ctx, const float *d_full, int which, int64_t n);  // own range of pos (0) / vel (1) -> published mirror

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include <cmath>
+#include <algorithm>
 
 namespace nbco {
 
@@ -158,7 +159,7 @@ direct3_scalar_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 template <int IPT, int BLOCK = kBlock, int UNROLL = 4>
 __global__ void __launch_bounds__(BLOCK)
 direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_begin, int64_t i_end,
-                      float *__restrict__ acc, const float *__restrict__ param, float eps2)
+                      float *__restrict__ acc, const float *__restrict__ param, float eps2, float *__restrict__ part = nullptr)
 {
 	static_assert(IPT % 2 == 0, "packed variant handles targets in pairs");
 	constexpr int NP = IPT / 2;
@@ -248,12 +249,31 @@ direct3_packed_kernel(const float4 *__restrict__ src, int64_t n_src, int64_t i_b
 			}
 			else
 			{
-				atomicAdd(acc + 3*i, scale * sum[k].sx);
-				atomicAdd(acc + 3*i + 1, scale * sum[k].sy);
-				atomicAdd(acc + 3*i + 2, scale * sum[k].sz);
+				// partial sum of this run of source tiles; combined in a fixed order by direct3_combine_kernel
+				float *o = part + 3 * ((int64_t)blockIdx.y * (i_end - i_begin) + (i - i_begin));
+				o[0] = sum[k].sx; o[1] = sum[k].sy; o[2] = sum[k].sz;
 			}
 		}
 	}
+}
+
+// acc[i] = scale * (partial sums of the source runs, added in run order with Kahan compensation): deterministic, and the
+// same for every sharding of the targets (the number of runs depends on the number of SOURCES only)
+__global__ void __launch_bounds__(256)
+direct3_combine_kernel(const float *__restrict__ part, int parts, int64_t i_begin, int64_t i_end, float *__restrict__ acc, const float *__restrict__ param)
+{
+	const int64_t cnt = i_end - i_begin;
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= cnt) return;
+	const float scale = param ? param[0] : 1.f;
+	Kahan3 s;
+	for (int y = 0; y < parts; ++y)
+	{
+		const float *o = part + 3 * ((int64_t)y * cnt + t);
+		s.add(o[0], o[1], o[2]);
+	}
+	float *a = acc + 3 * (i_begin + t);
+	a[0] = scale * s.sx; a[1] = scale * s.sy; a[2] = scale * s.sz;
 }
 
 // Pair potential sum_{i<j} (d^2+eps2)^(-1/2), accumulated in double (diagnostic, not a hot path).
@@ -352,23 +372,25 @@ int direct3_launch(nbco_ctx *ctx, const float *d_pos, float *d_acc, int64_t n, c
 		case 13: LAUNCH(direct3_packed_kernel, 4); break;
 		default: // <4, 256, 4>: measured fastest on B200 (profiles/r01_notes.md)
 		{
-			// grid: target blocks x source parts.  The target blocks alone leave the last wave partly empty (N = 2^20:
-			// 1024 blocks on 148 x occ slots; a rank of 8: 128 blocks on 148 SMs = 86 % of the chip), so the source
-			// range is cut into `parts` runs such that blocks x parts fills whole waves.
-			static int occ = 0;
-			if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, direct3_packed_kernel<4, 256, 4>, 256, 0) != cudaSuccess || occ < 1)) occ = 1;
-			const int64_t bx = (cnt + 256 * 4 - 1) / (256 * 4), slots = (int64_t)ctx->sm_count * occ;
+			// grid: target blocks x source runs.  The target blocks alone can leave most of the chip idle (a rank of 8 at
+			// N = 2^20: 128 blocks on 148 SMs; N = 8192: 8 blocks), so the source tiles are cut into `parts` runs, a
+			// function of the number of SOURCES only: every sharding of the targets adds the same partial sums in the same
+			// order (bit-identical shards, tests/test_direct_gpu.py), and there are no atomics.
+			const int64_t bx = (cnt + 256 * 4 - 1) / (256 * 4);
 			const int64_t tiles = (n + kTileJ - 1) / kTileJ;
-			int parts = 1;
-			double best = 0.0;
-			for (int sp = 1; sp <= 160 && sp * 8 <= tiles; ++sp)
+			const int parts = (int)std::min<int64_t>(16, tiles);
+			float *part = nullptr;
+			if (parts > 1)
 			{
-				const double waves = (double)(bx * sp) / (double)slots, eff = waves / std::ceil(waves);
-				if (eff > best + 0.01) { best = eff; parts = sp; }
-				if (best > 0.97) break;
+				NBCO_TRY(ctx->dpart.reserve(sizeof(float) * 3 * (size_t)parts * (size_t)cnt));
+				part = ctx->dpart.as<float>();
 			}
-			if (parts > 1) NBCO_CUDA(cudaMemsetAsync(d_acc + 3 * ib, 0, 12 * (size_t)cnt, ctx->stream));
-			direct3_packed_kernel<4, 256, 4><<<dim3((unsigned)bx, (unsigned)parts), 256, 0, ctx->stream>>>(src, n, ib, ie, d_acc, d_param, eps2);
+			direct3_packed_kernel<4, 256, 4><<<dim3((unsigned)bx, (unsigned)parts), 256, 0, ctx->stream>>>(src, n, ib, ie, d_acc, d_param, eps2, part);
+			if (parts > 1)
+			{
+				direct3_combine_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(part, parts, ib, ie, d_acc, d_param);
+				++ctx->launches;
+			}
 			break;
 		}
 #undef LAUNCH_P

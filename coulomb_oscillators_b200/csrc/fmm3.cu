@@ -10,11 +10,10 @@
 //  * the tree is the reference's: node i of level l owns sorted range [ceil(n i/2^l), ceil(n (i+1)/2^l)),
 //    split axis = widest box extent, child boxes cut at the boundary particles' coordinates.  index/mult
 //    are pure functions of (n, l, i) and are never stored.
-//  * build: only (fp32 key, u32 id) pairs are sorted.  Levels whose segments exceed kBottomCap
-//    particles run one stable segmented LSD radix sort each (4 x 8 bit, per-segment digit offsets,
-//    warp-match ranking); all remaining levels run in ONE kernel, a CTA per subtree holding its
-//    particles in shared memory (bitonic sort of 64-bit (key,slot) words in power-of-two blocks).
-//    Equal keys are ordered as a stable sort at every level would order them (ties fall back to
+//  * build (kdtree.cu): every level is a median SELECTION + unordered partition, not a sort.  Levels whose
+//    segments exceed kBottomCap particles: one histogram pass + one three-way partition pass over 16-byte
+//    (x, y, z, id) records; all remaining levels run in ONE kernel, a CTA per subtree holding its particles in
+//    shared memory.  Equal keys are ordered as a stable sort at every level would order them (ties fall back to
 //    the coordinates of the previous split axes, then the input index).  One gather at the end.
 //  * geometry that decides the interaction lists (centres, box sizes, MAC) is evaluated with the
 //    reference's host operation order and no FMA contraction (__fmul_rn/__fadd_rn), the MAC's
@@ -640,6 +639,14 @@ __global__ void __launch_bounds__(256) emit_kernel(const TravArgs a, const int2 
 	}
 }
 
+// end of every evaluation: fold "a list or a frontier did not fit" into a STICKY word (cnt[24]) that survives the
+// per-evaluation counter resets, so that evaluations which are only enqueued can be checked later (fmm3_harvest)
+__global__ void eval_check_kernel(u32 *cnt, u32 cap_list)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0)
+		if (cnt[0] > cap_list || cnt[1] > cap_list || cnt[5]) cnt[24] = 1u;
+}
+
 __global__ void traverse_init_kernel(int2 *front, u32 *cnt)
 {
 	if (threadIdx.x == 0 && blockIdx.x == 0)
@@ -748,7 +755,14 @@ struct FmmPlan
 	KdTree kd;
 	DevBuf center, mpole, local, tmp3, accn;
 	DevBuf p2p, m2l, frontA, frontB, cnt, mfac;
-	cudaEvent_t ev[PH_COUNT + 1];
+	// phase timers: a ring of event sets, one per evaluation in flight.  Evaluations between two tree rebuilds are only
+	// ENQUEUED (no host synchronisation); their event sets are read at the next synchronisation point (fmm3_harvest)
+	static constexpr int kEvRing = 16;
+	cudaEvent_t evr[kEvRing][PH_COUNT + 1];
+	int ev_head = 0, ev_npend = 0;      // sets [ev_head - ev_npend, ev_head) (mod kEvRing) await harvesting
+	bool ev_rebuild[kEvRing] = {};
+	cudaEvent_t *ev = nullptr;          // the set of the evaluation being enqueued
+	float last_ms[PH_COUNT] = {};
 	bool ev_ok = false, ev_valid = false;
 	double tot_ms[PH_COUNT] = {};
 	int64_t tot_evals = 0, tot_rebuilds = 0;
@@ -777,7 +791,9 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	FmmPlan &p = *ctx->fmm;
 	if (!p.ev_ok)
 	{
-		for (int i = 0; i <= PH_COUNT; ++i) NBCO_CUDA(cudaEventCreate(&p.ev[i]));
+		for (int k = 0; k < FmmPlan::kEvRing; ++k)
+			for (int i = 0; i <= PH_COUNT; ++i) NBCO_CUDA(cudaEventCreate(&p.evr[k][i]));
+		p.ev = p.evr[0];
 		p.ev_ok = true;
 	}
 	if (p.n == n && p.order == c.order && p.dens == c.dens_inhom && p.max_level == c.max_level) return NBCO_OK;
@@ -806,6 +822,7 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
 	p.queue_clean = false; p.rec_valid = false;
 	NBCO_TRY(p.cnt.reserve(128)); NBCO_TRY(p.mfac.reserve(4 * 2 * 40));
+	NBCO_CUDA(cudaMemsetAsync(p.cnt.p, 0, 128, ctx->stream)); // cnt[24] (sticky overflow) is never reset by the kernels
 	// MAC factor table: M = pow(mult / N, 1/(3p+6)) evaluated with the host libm like the
 	// reference CPU path (:410); a node of level l holds floor(n/2^l) or floor(n/2^l)+1 particles
 	float tab[2 * 32];
@@ -827,6 +844,16 @@ bool fmm3_next_rebuilds(nbco_ctx *ctx, int64_t n)
 	const FmmPlan &p = *ctx->fmm;
 	if (p.n != n || p.order != c.order || p.dens != c.dens_inhom || p.max_level != c.max_level) return true;
 	return c.unsort || (p.counter % c.tree_steps == 0);
+}
+
+bool fmm3_rebuilds_in(nbco_ctx *ctx, int64_t n, int64_t k)
+// will the evaluation that comes k evaluations after the next one (k = 0: the next one) permute pos / vel?
+{
+	const nbco_config &c = ctx->cfg;
+	if (!ctx->fmm) return true;
+	const FmmPlan &p = *ctx->fmm;
+	if (p.n != n || p.order != c.order || p.dens != c.dens_inhom || p.max_level != c.max_level) return true;
+	return c.unsort || ((p.counter + k) % c.tree_steps == 0);
 }
 
 int fmm3_peer_buffers(nbco_ctx *ctx, int64_t n, void **center, void **mpole)
@@ -1051,6 +1078,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll,
 	             p.ev[PH_L2P]);
 	if (peer) NBCO_TRY(peer_barrier(ctx)); // nobody reads this rank's centres / multipoles / positions any more
+	eval_check_kernel<<<1, 32, 0, st>>>(a.cnt, p.cap_list); LAUNCHED(ctx);
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_COUNT], st));
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;
@@ -1070,17 +1098,28 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 	if ((1 << p.L) < ctx->cfg.world) { set_error("fmm3_kd: more ranks than leaves"); return NBCO_ERR_INVALID; }
 	if (p.L > 26) { set_error("fmm3_kd: depth %d exceeds the list encoding", p.L); return NBCO_ERR_INVALID; }
 	const bool rebuild = ctx->cfg.unsort || (p.counter % ctx->cfg.tree_steps == 0);
+	const OrderOps *ops = order_ops(p.order);
+	if (!ops) { set_error("order %d not instantiated", p.order); return NBCO_ERR_INVALID; }
+	// Host synchronisation policy.  A rebuild evaluation is synchronised: its counters size the lists (grown with 2x
+	// headroom, the evaluation is then repeated) and all pending phase timers are read.  The evaluations that reuse
+	// the partition are only enqueued -- their lists differ from the rebuild evaluation's by a few per cent -- and a
+	// sticky device flag reports a list that did not fit at the next synchronisation point (fmm3_harvest; every public
+	// entry point ends with one).  NBCO_SYNC_EVERY_EVAL=1 restores one synchronisation per evaluation.
+	static int sync_all = -1;
+	if (sync_all < 0) { const char *e = getenv("NBCO_SYNC_EVERY_EVAL"); sync_all = (e && atoi(e)) ? 1 : 0; }
+	const bool must_sync = rebuild || sync_all || p.ev_npend >= FmmPlan::kEvRing - 1 || getenv("NBCO_DEBUG_TRAV");
 	bool do_build = rebuild;
 	for (int attempt = 0; attempt < 6; ++attempt)
 	{
-		const OrderOps *ops = order_ops(p.order);
-		if (!ops) { set_error("order %d not instantiated", p.order); return NBCO_ERR_INVALID; }
+		p.ev = p.evr[p.ev_head];
+		p.ev_rebuild[p.ev_head] = do_build;
 		int s = run_phases(*ops, ctx, p, d_pos, d_acc, d_param, fuse_elastic, do_build);
 		NBCO_TRY(s);
-		u32 h[6], perr = 0;
-		NBCO_CUDA(cudaMemcpyAsync(h, p.cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-		if (ctx->peer.active) NBCO_CUDA(cudaMemcpyAsync(&perr, (const char *)ctx->peer.pub.p + 512, 4, cudaMemcpyDeviceToHost, ctx->stream));
-		NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
+		p.ev_head = (p.ev_head + 1) % FmmPlan::kEvRing; ++p.ev_npend;
+		p.rebuilt = rebuild;
+		if (!must_sync) { ++p.counter; return NBCO_OK; }
+		int over = 0;
+		NBCO_TRY(fmm3_harvest(ctx, &over));
 		if (getenv("NBCO_DEBUG_TRAV"))
 		{
 			u32 dbg[20];
@@ -1088,17 +1127,9 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 			fprintf(stderr, "trav: p2p %u m2l %u records %u changed %u seeds %u retire-rounds %u retired %u rec-rounds %u\n", dbg[0], dbg[1], dbg[11],
 			        dbg[12], dbg[16], dbg[13], dbg[14], dbg[15]);
 		}
-		if (perr) { set_error("peer barrier timed out: a rank did not arrive (results of this evaluation are invalid)"); return NBCO_ERR_CUDA; }
-		p.ev_valid = true;
-		p.rebuilt = rebuild;
-		for (int k = 0; k < PH_COUNT; ++k)
-		{
-			float ms = 0.f;
-			if (cudaEventElapsedTime(&ms, p.ev[k], p.ev[k + 1]) == cudaSuccess) p.tot_ms[k] += ms;
-		}
-		++p.tot_evals; p.tot_rebuilds += do_build ? 1 : 0;
-		p.p2p_n = h[0]; p.m2l_n = h[1];
-		if (h[0] <= p.cap_list && h[1] <= p.cap_list && h[5] == 0)
+		// headroom for the enqueued evaluations that follow: lists at most half full after a rebuild
+		const bool roomy = 2 * p.p2p_n <= (int64_t)p.cap_list && 2 * p.m2l_n <= (int64_t)p.cap_list;
+		if (!over && (roomy || !rebuild || ctx->peer.active))
 		{
 			++p.counter;
 			return NBCO_OK;
@@ -1106,12 +1137,12 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 		if (ctx->peer.active)
 		{
 			// the ranks pass the peer barriers in lockstep: an evaluation cannot be repeated by one rank alone
-			set_error("peer mode: interaction lists exceed capacity (%u p2p, %u m2l of %u)", h[0], h[1], p.cap_list);
+			set_error("peer mode: interaction lists exceed capacity (%lld p2p, %lld m2l of %u)", (long long)p.p2p_n, (long long)p.m2l_n, p.cap_list);
 			return NBCO_ERR_OVERFLOW;
 		}
-		// a list or a frontier did not fit: grow and redo this evaluation.  With unsort == 0 the
-		// caller's arrays are already in tree order and the tree is valid: do not build again.
-		if (p.cap_list >= 0x7fffffffu / 2) break;
+		// a list or a frontier did not fit (or is more than half full): grow and redo this evaluation.  With
+		// unsort == 0 the caller's arrays are already in tree order and the tree is valid: do not build again.
+		if (p.cap_list >= 0x7fffffffu / 2) { if (!over) { ++p.counter; return NBCO_OK; } break; }
 		p.cap_list *= 2; p.cap_front = p.cap_list;
 		NBCO_TRY(p.p2p.reserve(8 * (size_t)p.cap_list)); NBCO_TRY(p.m2l.reserve(8 * (size_t)p.cap_list));
 		NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
@@ -1120,6 +1151,50 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 	}
 	set_error("interaction lists exceed capacity (%lld p2p, %lld m2l)", (long long)p.p2p_n, (long long)p.m2l_n);
 	return NBCO_ERR_OVERFLOW;
+}
+
+// Synchronisation point: wait for the stream, read the counters of the last evaluation and the sticky flags, collect
+// the phase timers of every evaluation enqueued since the previous call.  *overflow (optional) = the LAST evaluation's
+// lists did not fit; an overflow of an earlier, already accepted evaluation is an error (its results were used).
+int fmm3_harvest(nbco_ctx *ctx, int *overflow)
+{
+	if (overflow) *overflow = 0;
+	if (!ctx->fmm) return NBCO_OK;
+	FmmPlan &p = *ctx->fmm;
+	if (p.ev_npend == 0 || !p.cnt.p) return NBCO_OK;
+	u32 h[25] = {};
+	NBCO_CUDA(cudaMemcpyAsync(h, p.cnt.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
+	unsigned perr = 0;
+	if (ctx->peer.active) NBCO_TRY(peer_report_error(ctx, &perr));
+	const int npend = p.ev_npend;
+	for (int k = 0; k < npend; ++k)
+	{
+		const int set = (p.ev_head - npend + k + 2 * FmmPlan::kEvRing) % FmmPlan::kEvRing;
+		for (int q = 0; q < PH_COUNT; ++q)
+		{
+			float ms = 0.f;
+			if (cudaEventElapsedTime(&ms, p.evr[set][q], p.evr[set][q + 1]) == cudaSuccess) { p.tot_ms[q] += ms; p.last_ms[q] = ms; }
+		}
+		++p.tot_evals; p.tot_rebuilds += p.ev_rebuild[set] ? 1 : 0;
+	}
+	p.ev_npend = 0;
+	p.ev_valid = true;
+	p.p2p_n = h[0]; p.m2l_n = h[1];
+	if (perr) { set_error("peer barrier timed out: a rank did not arrive (results since the last synchronisation are invalid)"); return NBCO_ERR_CUDA; }
+	const bool last_over = h[0] > p.cap_list || h[1] > p.cap_list || h[5] != 0;
+	if (h[24])
+	{
+		NBCO_CUDA(cudaMemsetAsync((u32 *)p.cnt.p + 24, 0, 4, ctx->stream));
+		if (npend > 1 || !overflow)
+		{
+			set_error("interaction lists overflowed during an enqueued tree-reuse evaluation (%u p2p, %u m2l of %u): results since the last "
+			          "synchronisation are invalid; rerun with NBCO_SYNC_EVERY_EVAL=1", h[0], h[1], p.cap_list);
+			return NBCO_ERR_OVERFLOW;
+		}
+	}
+	if (overflow) *overflow = last_over ? 1 : 0;
+	return NBCO_OK;
 }
 
 extern const OrderOps kOrderOps1, kOrderOps2, kOrderOps3, kOrderOps4, kOrderOps5, kOrderOps6, kOrderOps7, kOrderOps8, kOrderOps9, kOrderOps10;
@@ -1149,7 +1224,9 @@ void fmm3_destroy(nbco_ctx *ctx)
 	kd_release(p.kd);
 	DevBuf *all[] = {&p.center, &p.mpole, &p.local, &p.tmp3, &p.accn, &p.p2p, &p.m2l, &p.frontA, &p.frontB, &p.cnt, &p.mfac};
 	for (DevBuf *b : all) b->release();
-	if (p.ev_ok) for (int i = 0; i <= PH_COUNT; ++i) cudaEventDestroy(p.ev[i]);
+	if (p.ev_ok)
+		for (int k = 0; k < FmmPlan::kEvRing; ++k)
+			for (int i = 0; i <= PH_COUNT; ++i) cudaEventDestroy(p.evr[k][i]);
 	delete ctx->fmm;
 	ctx->fmm = nullptr;
 }
@@ -1235,23 +1312,20 @@ int nbco_fmm_get_lists(nbco_ctx *ctx, int32_t *h_p2p, int64_t p2p_cap, int32_t *
 
 int nbco_fmm_get_phase_ms(nbco_ctx *ctx, const char **names, float *ms, int cap)
 {
-	if (!ctx || !ctx->fmm || !ctx->fmm->ev_valid) return 0;
-	FmmPlan &p = *ctx->fmm;
+	if (!ctx || !ctx->fmm) return 0;
 	cudaSetDevice(ctx->cfg.device);
-	cudaStreamSynchronize(ctx->stream);
+	if (fmm3_harvest(ctx, nullptr) != NBCO_OK || !ctx->fmm->ev_valid) return 0;
+	FmmPlan &p = *ctx->fmm;
 	int k = 0;
-	for (; k < PH_COUNT && k < cap; ++k)
-	{
-		names[k] = kPhaseNames[k];
-		ms[k] = 0.f;
-		cudaEventElapsedTime(&ms[k], p.ev[k], p.ev[k + 1]);
-	}
+	for (; k < PH_COUNT && k < cap; ++k) { names[k] = kPhaseNames[k]; ms[k] = p.last_ms[k]; }
 	return k;
 }
 
 int nbco_fmm_phase_totals(nbco_ctx *ctx, const char **names, double *ms, int cap, int64_t *h_evals, int reset)
 {
 	if (!ctx || !ctx->fmm) return 0;
+	cudaSetDevice(ctx->cfg.device);
+	if (fmm3_harvest(ctx, nullptr) != NBCO_OK) return 0;
 	FmmPlan &p = *ctx->fmm;
 	int k = 0;
 	for (; k < PH_COUNT && k < cap; ++k) { names[k] = kPhaseNames[k]; ms[k] = p.tot_ms[k]; }

@@ -11,10 +11,8 @@ typedef unsigned long long u64;
 typedef unsigned int u32;
 typedef unsigned short u16;
 
-constexpr int kTile = 4096;        // elements per radix tile (256 threads x 16)
 constexpr int kBottomCap = 8192;   // particles a bottom CTA keeps in shared memory
 constexpr int kBottomThreads = 1024;
-constexpr u32 kSlotMask = 0x1FFFu; // 13 bits: slot inside a bottom CTA
 constexpr int kNoAxis = 3;
 constexpr int kFlagShift = 28;             // interaction-list entries carry two target flags above the node id
 constexpr int kNodeMask = (1 << kFlagShift) - 1;
@@ -128,7 +126,9 @@ struct KdTree
 	int64_t n = 0;
 	int L = 0, lt = 0;
 	DevBuf lbound, rbound, size2, splitdim, chain;   // per node
-	DevBuf keys, idxA, idxB, tie, hist, sel, cur, spos, perm, bbox, soa;
+	DevBuf payA, payB;   // (x, y, z, id) records, ping-pong between the top levels (16 B / particle each)
+	DevBuf hist, seg;    // per-segment linear histograms and selection state of the current top level
+	DevBuf spos, perm, bbox;
 	bool bottom_attr = false;
 };
 int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L);

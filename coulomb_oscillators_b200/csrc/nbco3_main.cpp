@@ -237,8 +237,9 @@ int main(int argc, const char **argv)
 			if (nbco_force_fmm3_kd(d.ctx, d.buf, d.tmp, n, d.par)) return fail(nbco_last_error());
 			if (nbco_force_direct3(d.ctx, d.buf, d_acc, n, d.par)) return fail(nbco_last_error());
 			if (nbco_mean_rel_err(d.ctx, d.tmp, d_acc, n, &err, nullptr)) return fail(nbco_last_error());
-			// pre_symplectic_euler over add_elastic alone (main3.cu:820-826): a = -k x; v += a dt; x += v dt
-			CU(cudaMemset(d_acc, 0, vb));
+			// pre_symplectic_euler(add_elastic, ...) (main3.cu:820-826, integrator.cuh:50-66): add_elastic SUBTRACTS k x from the
+			// acc buffer, which test_accuracy left holding the direct-sum Coulomb field (main3.cu:172-173): the particles step
+			// under Coulomb + elastic force:  a -= k x; v += a dt; x += v dt
 			CK(nbco_add_elastic(d.ctx, d.buf, d_acc, n, d.par + 3));
 			CK(nbco_step(d.ctx, d.buf + 3 * n, d_acc, dt, n));
 			CK(nbco_step(d.ctx, d.buf, d.buf + 3 * n, dt, n));

@@ -210,6 +210,41 @@ class Ref:
         return t
 
 
+REF64_SO = os.path.join(ROOT, "oracle", "_ref", "libnbco_ref_f64.so")
+
+
+class Ref64:
+    """the unmodified reference compiled with SCAL = double (oracle/ref_harness_f64.cu): fp64 ground truth"""
+    _lib = None
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF64_SO)
+
+    def __init__(self, order=3, radius=1.0, eps2=1e-18, dens_inhom=1.0, threads=None, coll=1):
+        if Ref64._lib is None:
+            L = C.CDLL(REF64_SO)
+            L.ref64_config.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+            L.ref64_eval.argtypes = [C.c_int, _d, _d, C.c_int, C.c_void_p]
+            Ref64._lib = L
+        self.cfg = (order, radius, eps2, dens_inhom, threads or min(os.cpu_count() or 8, 64), coll)
+
+    def _eval(self, which, pos, param):
+        n = pos.shape[0]
+        p64 = np.ascontiguousarray(pos, np.float64).ravel()
+        acc = np.zeros(3 * n, np.float64)
+        par = None if param is None else np.ascontiguousarray(param, np.float64)
+        self._lib.ref64_config(*self.cfg)
+        assert self._lib.ref64_eval(which, p64, acc, n, _ptr(par)) == 0
+        return acc.reshape(n, 3)
+
+    def fmm3(self, pos, param=None):
+        return self._eval(1, pos, param)
+
+    def direct3(self, pos, param=None):
+        return self._eval(0, pos, param)
+
+
 def unique_axes(pos):
     """make every coordinate of every axis distinct (bump duplicates by one ulp until strictly
     increasing): on such inputs the reference's unstable sorts have a unique answer.
