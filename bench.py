@@ -89,9 +89,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-SINGLE_KERNEL_PHASES = {"kd_bottom": "kd_bottom_kernel", "p2p": "p2p_kernel", "m2l": "m2l_kernel", "l2p": "l2p_kernel"}
-# DRAM bytes per launch from `ncu --set full` captures of this round (profiles/r01_notes.md); None = not captured
-NCU_TRAFFIC = {"kd_bottom": {"n": 1 << 24, "bytes": 1.690451e9 + 421.263616e6}}
+# single-kernel phases (their CUDA-event time is one kernel launch).  Orders 1..6 run the by-target flow (round 2): the
+# "p2p" phase is the bucketing of the lists by target (6 small kernels), "m2l" is empty (the M2L sums are gathered inside
+# the "l2l" levels) and "l2p" = L2P + near field in one kernel.
+SINGLE_KERNEL_PHASES = {"kd_bottom": "kd_bottom_kernel", "l2p": "l2p_near_kernel"}
+SINGLE_KERNEL_PHASES_PAIRS = {"kd_bottom": "kd_bottom_kernel", "p2p": "p2p_kernel", "m2l": "m2l_kernel", "l2p": "l2p_kernel"}
+# DRAM bytes per launch from `ncu --set full` captures of this round (profiles/r02_notes.md); None = not captured
+NCU_TRAFFIC = {"kd_bottom": {"n": 1 << 24, "bytes": 272.42368e6 + 367.023872e6}}
 
 
 def kd_top_levels(n, L, cap=8192):
@@ -102,7 +106,12 @@ def kd_top_levels(n, L, cap=8192):
     return min(lt, L - 1)
 
 
-def fmm_bytes_per_eval(n, order, L, p2p_pairs, m2l_pairs):
+def by_target_flow(order):
+    """cfg.reproducible (lists bucketed by target, no atomics) is opt-in and slower; the bench runs the default pair flow"""
+    return False
+
+
+def fmm_bytes_per_eval(n, order, L, p2p_pairs, m2l_pairs, survey_model=False):
     """algorithmic bytes of one FMM evaluation per phase.  The survey's
     rebuild figure (16 L + 52) N is apportioned by level count between the global levels (kd_top), the
     shared-memory levels (kd_bottom) and the final permutation of pos/vel (permute, 40 N)."""
@@ -110,7 +119,7 @@ def fmm_bytes_per_eval(n, order, L, p2p_pairs, m2l_pairs):
     SM = 4 * order * (order + 1) * (order + 2) // 6
     SL = 4 * (order + 1) ** 2
     lt = kd_top_levels(n, L)
-    return {
+    b = {
         "kd_top": (16 * lt + 12) * n,
         "kd_bottom": 16 * (L - lt) * n,
         "permute": 40 * n,
@@ -121,6 +130,15 @@ def fmm_bytes_per_eval(n, order, L, p2p_pairs, m2l_pairs):
         "l2l": Nn * (12 + 2 * SL),
         "l2p": Nl * (12 + SL) + 36 * n,
     }
+    if by_target_flow(order) and not survey_model:
+        # same algorithmic bytes, attributed to the phases that now do the work: the levels gather the M2L sums (m2l + l2l),
+        # the leaf kernel gathers the near field (l2p + p2p), "p2p" = bucketing the lists (read twice, 4 B per directed entry, row offsets)
+        pairs = m2l_pairs + p2p_pairs
+        b["l2l"] = b["l2l"] + b["m2l"]
+        b["l2p"] = b["l2p"] + b["p2p"]
+        b["p2p"] = 16 * pairs + 8 * pairs + 8 * (Nn + Nl)
+        b["m2l"] = 0
+    return b
 
 
 REBUILD_PHASES = ("kd_top", "kd_bottom", "permute")
@@ -289,20 +307,22 @@ def run_ours(args):
     total_ms = max(sum(totals.values()), 1e-9)
     for k, tot in totals.items():
         calls = rebuilds if k in REBUILD_PHASES else evals
-        if calls == 0:
+        if calls == 0 or bytes_eval.get(k, 0) == 0:
             continue
         avg_ms = tot / calls
         phases[k] = {"avg_ms": round(avg_ms, 4), "launches": int(calls), "share": round(tot / total_ms, 4),
                      "GBps": round(bytes_eval[k] / (avg_ms * 1e-3) / 1e9, 1) if avg_ms > 0 else None}
     # ---- roofline of the dominant KERNEL: the single-kernel phase with the largest total time ----
-    dom = max(SINGLE_KERNEL_PHASES, key=lambda k: totals.get(k, 0.0))
+    single = SINGLE_KERNEL_PHASES if by_target_flow(order) else SINGLE_KERNEL_PHASES_PAIRS
+    dom = max(single, key=lambda k: totals.get(k, 0.0))
     dcalls = rebuilds if dom in REBUILD_PHASES else evals
     dom_ms = totals[dom] / max(dcalls, 1)
     achieved = bytes_eval[dom] / (dom_ms * 1e-3) / 1e9
     tr = NCU_TRAFFIC.get(dom)
-    step_bytes = world * (sum(v for k, v in bytes_eval.items() if k not in REBUILD_PHASES)
-                          + sum(bytes_eval[k] for k in REBUILD_PHASES) / 8) + 60 * n
-    roofline = {"bound": "hbm", "kernel": SINGLE_KERNEL_PHASES[dom], "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
+    # whole step against HBM: SURVEY.md section 8(d)'s model unchanged (the list bucketing of the by-target flow is overhead, not work)
+    sv = fmm_bytes_per_eval(n, order, info.levels, info.p2p_pairs * world, info.m2l_pairs * world, survey_model=True)
+    step_bytes = sum(v for k, v in sv.items() if k not in REBUILD_PHASES) + sum(sv[k] for k in REBUILD_PHASES) / 8 + 60 * n
+    roofline = {"bound": "hbm", "kernel": single[dom], "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": round(achieved / peaks["hbm_gbs"], 4),
                 "traffic": tr["bytes"] if tr and tr["n"] == n else None, "peak_kind": peak_kind,
                 "avg_launch_ms": round(dom_ms, 4), "launches": int(dcalls),

@@ -21,7 +21,8 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("order", C.c_int32), ("radius", C.c_float), ("eps2", C.c_float),
                 ("dens_inhom", C.c_float), ("max_level", C.c_int32), ("tree_steps", C.c_int32),
                 ("coll", C.c_int32), ("unsort", C.c_int32), ("m2l_first", C.c_int32),
-                ("rank", C.c_int32), ("world", C.c_int32), ("eps2_d", C.c_double)]
+                ("rank", C.c_int32), ("world", C.c_int32), ("eps2_d", C.c_double),
+                ("reproducible", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class FmmInfo(C.Structure):
@@ -48,7 +49,7 @@ SYMBOLS = [
     "nbco_fmm2_levels", "nbco_fmm2_get_info", "nbco_fmm2_get_tree", "nbco_fmm2_get_phase_ms",
     "nbco_init_ga2", "nbco_init_kv2", "nbco_beam_params2", "nbco_state_read2", "nbco_state_write2",
     "nbco_peer_export", "nbco_peer_attach", "nbco_peer_attach_local", "nbco_peer_commit", "nbco_peer_barrier", "nbco_peer_gather", "nbco_peer_detach",
-    "nbco_shard_range", "nbco_init_ga", "nbco_init_test_cube", "nbco_state_read", "nbco_state_write", "nbco_free",
+    "nbco_track_ids", "nbco_shard_range", "nbco_init_ga", "nbco_init_test_cube", "nbco_state_read", "nbco_state_write", "nbco_free",
 ]
 
 
@@ -79,6 +80,7 @@ def _load():
     L.nbco_eval_host.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp]
     L.nbco_run_host.argtypes = [vp, C.c_int, C.c_int, vp, vp, i64, vp, f64, i64]
     L.nbco_step_host.argtypes = [vp, C.c_int, C.c_int, vp, i64, vp, f64, i64]
+    L.nbco_track_ids.argtypes = [vp, vp]
     L.nbco_fmm_get_info.argtypes = [vp, C.POINTER(FmmInfo)]
     L.nbco_fmm_get_tree.argtypes = [vp] + [vp] * 9
     L.nbco_fmm_get_lists.argtypes = [vp, vp, i64, vp, i64]
@@ -323,6 +325,10 @@ class Context:
         m2l = np.empty((i.m2l_pairs, 2), np.int32)
         _check(lib.nbco_fmm_get_lists(self._h, _hp(p2p), i.p2p_pairs, _hp(m2l), i.m2l_pairs))
         return p2p, m2l
+
+    def track_ids(self, d_ids):
+        """device pointer to n int32 ids that follow the particles through the tree rebuilds (0 / None: stop)"""
+        _check(lib.nbco_track_ids(self._h, C.c_void_p(d_ids or 0)))
 
     def fmm_phase_totals(self, reset=False):
         """({phase: total ms}, evaluations, rebuilds) since the last reset"""

@@ -84,12 +84,17 @@ static int sync(nbco_ctx *ctx)
 }
 
 // One step of a scheme, enqueued on the context stream (no host synchronisation inside).
-static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64_t n, const float *param, float dtf)
+// [lo, hi): the particles this context advances (peer mode: the rank's own tree-order range; else everything)
+static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64_t n, const float *param, float dtf, int64_t lo, int64_t hi)
 {
 	float *pos = buf, *vel = buf + 3*n, *acc = buf + 6*n;
 	const long double dt = dtf, ds = dt * 1.0L; // scale = 1 everywhere in the reference
-	auto K = [&](long double c) { return step_launch(ctx, vel, acc, (float)c, n); };
-	auto D = [&](long double c) { return step_launch(ctx, pos, vel, (float)c, n); };
+	auto K = [&](long double c) { return step_launch(ctx, vel + 3*lo, acc + 3*lo, (float)c, hi - lo); };
+	auto D = [&](long double c)
+	{
+		if (ctx->peer.active) ctx->peer.have_full = false; // the other ranges of this rank's arrays are stale from here on
+		return step_launch(ctx, pos + 3*lo, vel + 3*lo, (float)c, hi - lo);
+	};
 	auto F = [&]() { return eval_dispatch(ctx, evaluator, pos, acc, n, param); };
 	switch (scheme)
 	{
@@ -129,20 +134,19 @@ static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int
 static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64_t n, const float *param, float dtf, int64_t nsteps,
                      cudaEvent_t ev_last_drift = nullptr)
 {
-	if (ctx->peer.active && scheme != NBCO_LEAPFROG) { set_error("peer mode integrates with the leapfrog scheme only"); return NBCO_ERR_INVALID; }
+	// peer mode (peer.cu): every rank steps its own tree-order range; the evaluator exchanges what it needs
+	int64_t lo = 0, hi = n;
+	const bool fmm = evaluator == NBCO_EVAL_FMM3_KD || evaluator == NBCO_EVAL_COULOMB_FMM3_KD;
+	if (ctx->peer.active && fmm) nbco_shard_range(n, ctx->cfg.rank, ctx->cfg.world, &lo, &hi);
 	if (scheme != NBCO_LEAPFROG || nsteps <= 0)
 	{
 		for (int64_t s = 0; s < nsteps; ++s)
-			NBCO_TRY(scheme_step(ctx, scheme, evaluator, buf, n, param, dtf));
+			NBCO_TRY(scheme_step(ctx, scheme, evaluator, buf, n, param, dtf, lo, hi));
 		return NBCO_OK;
 	}
 	float *pos = buf, *vel = buf + 3*n, *acc = buf + 6*n;
 	const long double dt = dtf;
 	const float h = (float)(dt * 1.0L * 0.5L);
-	// peer mode (peer.cu): every rank steps its own tree-order range; the evaluator exchanges what it needs
-	int64_t lo = 0, hi = n;
-	const bool fmm = evaluator == NBCO_EVAL_FMM3_KD || evaluator == NBCO_EVAL_COULOMB_FMM3_KD;
-	if (ctx->peer.active && fmm) nbco_shard_range(n, ctx->cfg.rank, ctx->cfg.world, &lo, &hi);
 	for (int64_t s = 0; s < nsteps; ++s)
 	{
 		NBCO_TRY(kick_drift_launch(ctx, pos + 3*lo, vel + 3*lo, acc + 3*lo, h, h, s > 0, dtf, hi - lo));
@@ -178,6 +182,7 @@ void nbco_default_config(nbco_config *cfg)
 	cfg->rank = 0;
 	cfg->world = 1;
 	cfg->eps2_d = 1.e-18;    // EPS2 with SCAL = double (2D path)
+	cfg->reproducible = 0;
 }
 
 int nbco_abi_version(void) { return NBCO_ABI_VERSION; }
@@ -245,6 +250,14 @@ int nbco_get_config(const nbco_ctx *ctx, nbco_config *cfg)
 }
 
 void *nbco_stream(nbco_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int nbco_track_ids(nbco_ctx *ctx, int32_t *d_ids)
+{
+	if (!ctx) { set_error("null context"); return NBCO_ERR_INVALID; }
+	if (d_ids && ctx->peer.active) { set_error("nbco_track_ids is not available while peers are attached"); return NBCO_ERR_INVALID; }
+	ctx->ids = d_ids;
+	return NBCO_OK;
+}
 
 #define ENTER(ctx)                                                         \
 	if (!(ctx)) { set_error("null context"); return NBCO_ERR_INVALID; }    \

@@ -81,6 +81,8 @@ struct nbco_ctx
 	cudaStream_t copy_stream = nullptr;   // nbco_step_host: read-back of the positions overlaps the force evaluation
 	cudaEvent_t ev_drift = nullptr, ev_copied = nullptr;
 
+	int32_t *ids = nullptr;   // nbco_track_ids: permuted with pos / vel at every rebuild (unsort = 0)
+
 	nbco::FmmPlan *fmm = nullptr;
 	nbco::PeerState peer;
 	nbco::Fmm2Plan *fmm2 = nullptr;

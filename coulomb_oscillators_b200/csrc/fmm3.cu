@@ -43,6 +43,12 @@ __global__ void __launch_bounds__(256) gather3_kernel(const float *__restrict__ 
 	}
 }
 
+__global__ void __launch_bounds__(256) gather1_kernel(const int *__restrict__ src, const int *__restrict__ perm, int *__restrict__ dst, int64_t n)
+{
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) dst[j] = src[perm[j]];
+}
+
 // peer mode: the velocity of sorted particle j comes from whoever held its pre-rebuild index (tree-order ranges
 // are fixed index ranges, so that is rank floor(2^g idx / n)); most particles stay on their rank between rebuilds
 struct VelSrc { const float *v[kMaxPeers]; int g, me; };
@@ -657,6 +663,139 @@ __global__ void traverse_init_kernel(int2 *front, u32 *cnt)
 }
 
 // =====================================================================================
+//  interaction lists bucketed by target (CsrView, fmm3_common.cuh): count, scan, fill, sort
+// =====================================================================================
+// target id of the directed interactions of list entry w: M2L entries come first, then the P2P entries
+struct CsrArgs
+{
+	const int2 *m2l, *p2p;
+	const u32 *cnt;          // [0] p2p pairs, [1] m2l pairs
+	u32 cap_list;
+	u32 *deg, *off, *bsum;
+	int *src;
+	u32 cap_src;
+	int ntot, nrows, leaf_beg; // nrows = ntot + 2^L
+	u32 *sticky;             // cnt + 5: something did not fit
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) csr_count_fill_kernel(CsrArgs a)
+{
+	const u32 nm = min(a.cnt[1], a.cap_list), np = min(a.cnt[0], a.cap_list);
+	for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < nm + np; w += gridDim.x * blockDim.x)
+	{
+		const bool is_m = w < nm;
+		int2 pr = is_m ? a.m2l[w] : a.p2p[w - nm];
+		const int flags = (pr.x >> kFlagShift) & 3; // bit 0: pr.x is a target of this rank, bit 1: pr.y
+		pr.x &= kNodeMask;
+		const int rowx = is_m ? pr.x : a.ntot + (pr.x - a.leaf_beg), rowy = is_m ? pr.y : a.ntot + (pr.y - a.leaf_beg);
+		if (flags & 1)
+		{
+			if (!FILL) atomicAdd(a.deg + rowx, 1u);
+			else
+			{
+				// the counters run back to zero while the rows fill: ready for the next evaluation without a memset
+				const u32 pos = a.off[rowx] + (atomicSub(a.deg + rowx, 1u) - 1u);
+				if (pos < a.cap_src) a.src[pos] = pr.y;
+			}
+		}
+		if (flags & 2)
+		{
+			if (!FILL) atomicAdd(a.deg + rowy, 1u);
+			else
+			{
+				const u32 pos = a.off[rowy] + (atomicSub(a.deg + rowy, 1u) - 1u);
+				if (pos < a.cap_src) a.src[pos] = pr.x;
+			}
+		}
+	}
+}
+
+constexpr int kScanBlock = 1024, kScanPer = 4, kScanTile = kScanBlock * kScanPer;
+
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *wsum /* 32 */, u32 &total)
+{
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	u32 incl = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+	__syncthreads(); // wsum may still be read from a previous call
+	if (lane == 31) wsum[w] = incl;
+	__syncthreads();
+	u32 base = 0, tot = 0;
+	for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { const u32 x = wsum[i]; if (i < w) base += x; tot += x; }
+	total = tot;
+	return base + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanBlock) csr_scan_sums_kernel(CsrArgs a)
+{
+	__shared__ u32 wsum[32];
+	const int64_t i0 = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanPer;
+	u32 s = 0;
+#pragma unroll
+	for (int k = 0; k < kScanPer; ++k) if (i0 + k < a.nrows) s += a.deg[i0 + k];
+	u32 total;
+	block_exclusive_scan(s, wsum, total);
+	if (threadIdx.x == 0) a.bsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanBlock) csr_scan_top_kernel(CsrArgs a, int nblocks)
+{
+	__shared__ u32 wsum[32];
+	__shared__ u32 carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int b0 = 0; b0 < nblocks; b0 += kScanBlock)
+	{
+		const int b = b0 + threadIdx.x;
+		const u32 v = b < nblocks ? a.bsum[b] : 0u;
+		u32 total;
+		const u32 ex = block_exclusive_scan(v, wsum, total);
+		const u32 c = carry;
+		if (b < nblocks) a.bsum[b] = c + ex;
+		__syncthreads();
+		if (threadIdx.x == 0) carry = c + total;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		a.off[a.nrows] = carry;
+		if (carry > a.cap_src) *a.sticky = 1u; // the host grows the row storage and repeats the evaluation
+	}
+}
+
+__global__ void __launch_bounds__(kScanBlock) csr_scan_apply_kernel(CsrArgs a)
+{
+	__shared__ u32 wsum[32];
+	const int64_t i0 = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanPer;
+	u32 d[kScanPer], s = 0;
+#pragma unroll
+	for (int k = 0; k < kScanPer; ++k) { d[k] = i0 + k < a.nrows ? a.deg[i0 + k] : 0u; s += d[k]; }
+	u32 total;
+	u32 run = a.bsum[blockIdx.x] + block_exclusive_scan(s, wsum, total);
+#pragma unroll
+	for (int k = 0; k < kScanPer; ++k) { if (i0 + k < a.nrows) a.off[i0 + k] = run; run += d[k]; }
+}
+
+// rows in ascending source order: the sums of the downward pass do not depend on the order in which the traversal
+// emitted the pairs (run-to-run reproducible forces).  Rows are short (a few entries; at most some tens).
+__global__ void __launch_bounds__(256) csr_sort_kernel(CsrArgs a)
+{
+	for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < a.nrows; row += gridDim.x * blockDim.x)
+	{
+		const u32 b = a.off[row], e = min(a.off[row + 1], a.cap_src);
+		for (u32 i = b + 1; i < e; ++i)
+		{
+			const int v = a.src[i];
+			u32 j = i;
+			for (; j > b && a.src[j - 1] > v; --j) a.src[j] = a.src[j - 1];
+			a.src[j] = v;
+		}
+	}
+}
+
+// =====================================================================================
 //  near field (replaces fmm_p2p3_kdtree_coalesced / _self_, :874-959,1048-1120)
 // =====================================================================================
 __device__ __forceinline__ float rsqrt_approx(float x)
@@ -742,6 +881,8 @@ p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap
 // =====================================================================================
 enum Phase { PH_KDTOP = 0, PH_KDBOTTOM, PH_PERMUTE, PH_UPWARD, PH_TRAVERSE, PH_P2P, PH_M2L, PH_L2L, PH_L2P, PH_COUNT };
 // single-kernel phases: kd_bottom, p2p, m2l, l2p (their CUDA-event times are kernel launch durations)
+// by-target orders: "p2p" = bucketing the lists by target, "m2l" is empty (the M2L sums are gathered inside the "l2l" levels),
+// "l2p" includes the near field; pair-list orders (7..10): the phases are what their names say
 static const char *kPhaseNames[PH_COUNT] = {"kd_top", "kd_bottom", "permute", "p2m_m2m", "traverse", "p2p", "m2l", "l2l", "l2p"};
 
 struct FmmPlan
@@ -755,6 +896,9 @@ struct FmmPlan
 	KdTree kd;
 	DevBuf center, mpole, local, tmp3, accn;
 	DevBuf p2p, m2l, frontA, frontB, cnt, mfac;
+	DevBuf csr_deg, csr_off, csr_src, csr_bsum;   // lists bucketed by target (cfg.reproducible)
+	u32 cap_src = 0;
+	bool csr_ready = false;
 	// phase timers: a ring of event sets, one per evaluation in flight.  Evaluations between two tree rebuilds are only
 	// ENQUEUED (no host synchronisation); their event sets are read at the next synchronisation point (fmm3_harvest)
 	static constexpr int kEvRing = 16;
@@ -796,7 +940,7 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 		p.ev = p.evr[0];
 		p.ev_ok = true;
 	}
-	if (p.n == n && p.order == c.order && p.dens == c.dens_inhom && p.max_level == c.max_level) return NBCO_OK;
+	if (p.n == n && p.order == c.order && p.dens == c.dens_inhom && p.max_level == c.max_level && (p.csr_ready || !c.reproducible)) return NBCO_OK;
 	if (ctx->peer.active) { set_error("n / order / levels cannot change while peers are attached (published buffers would move)"); return NBCO_ERR_INVALID; }
 	if (n < 8) { set_error("fmm3_kd needs n >= 8 (got %lld)", (long long)n); return NBCO_ERR_INVALID; }
 	if (n >= (1ll << 31)) { set_error("n must be < 2^31"); return NBCO_ERR_INVALID; }
@@ -820,6 +964,20 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	}
 	NBCO_TRY(p.p2p.reserve(8 * (size_t)p.cap_list)); NBCO_TRY(p.m2l.reserve(8 * (size_t)p.cap_list));
 	NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
+	{
+		// by-target rows (cfg.reproducible): ntot + 2^L targets
+		const size_t nrows = nt + ((size_t)1 << L);
+		// storage: every pair of the two lists yields at most two directed entries
+		p.cap_src = (u32)std::min<int64_t>(4ll * p.cap_list, 0x7fffffff);
+		if (c.reproducible)
+		{
+			NBCO_TRY(p.csr_deg.reserve(4 * (nrows + 1))); NBCO_TRY(p.csr_off.reserve(4 * (nrows + 1)));
+			NBCO_TRY(p.csr_src.reserve(4 * (size_t)p.cap_src));
+			NBCO_TRY(p.csr_bsum.reserve(4 * ((nrows + kScanTile - 1) / kScanTile + 1)));
+			NBCO_CUDA(cudaMemsetAsync(p.csr_deg.p, 0, 4 * (nrows + 1), ctx->stream));
+		}
+		p.csr_ready = c.reproducible != 0;
+	}
 	p.queue_clean = false; p.rec_valid = false;
 	NBCO_TRY(p.cnt.reserve(128)); NBCO_TRY(p.mfac.reserve(4 * 2 * 40));
 	NBCO_CUDA(cudaMemsetAsync(p.cnt.p, 0, 128, ctx->stream)); // cnt[24] (sticky overflow) is never reset by the kernels
@@ -933,11 +1091,22 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 				gather3_kernel<<<grid_for(cnt, 256, ctx->sm_count, 8), 256, 0, st>>>(d_pos + 3*n, p.kd.perm.as<int>() + own_lo, p.tmp3.as<float>() + 3*own_lo, cnt);
 			LAUNCHED(ctx);
 			NBCO_CUDA(cudaMemcpyAsync(d_pos + 3*n + 3*own_lo, p.tmp3.as<float>() + 3*own_lo, 12 * (size_t)cnt, cudaMemcpyDeviceToDevice, st));
+			if (ctx->ids && !peer)
+			{
+				// optional identity array (nbco_track_ids): the same permutation as pos / vel
+				gather1_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(ctx->ids, p.kd.perm.as<int>(), p.tmp3.as<int>(), n);
+				LAUNCHED(ctx);
+				NBCO_CUDA(cudaMemcpyAsync(ctx->ids, p.tmp3.p, 4 * (size_t)n, cudaMemcpyDeviceToDevice, st));
+			}
 		}
 		if (peer) ps.have_full = false;
 	}
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_UPWARD], st));
-	NBCO_CUDA(cudaMemsetAsync(p.local.p, 0, sizeof(float) * (size_t)p.ntot * p.sL, st));
+	// by-target orders write every local exactly once (no zero-fill); pair-list orders accumulate with atomics
+	// (opt-in: cfg.reproducible.  Measured on B200 at N = 2^24: the gather per target is load-imbalanced -- rows hold 0..30
+	// sources -- and costs 2.3 ms per evaluation against 0.84 ms for the pair kernels: profiles/r02_notes.md)
+	const bool by_target = ops.by_target && c.reproducible;
+	if (!by_target) NBCO_CUDA(cudaMemsetAsync(p.local.p, 0, sizeof(float) * (size_t)p.ntot * p.sL, st));
 	if (peer) NBCO_TRY(peer_publish(ctx, d_pos, 0, n));
 	ops.upward(ctx, t, spos, n, L, pr, pg, 0);
 	if (peer)
@@ -1054,6 +1223,30 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	}
 
 	float *accn = p.accn.as<float>();
+	if (by_target)
+	{
+		// ---- lists bucketed by target: every local / acceleration becomes one sum in registers (no atomics) ----
+		NBCO_CUDA(cudaEventRecord(p.ev[PH_P2P], st));
+		CsrArgs ca;
+		ca.m2l = a.m2l; ca.p2p = a.p2p; ca.cnt = a.cnt; ca.cap_list = p.cap_list;
+		ca.deg = p.csr_deg.as<u32>(); ca.off = p.csr_off.as<u32>(); ca.bsum = p.csr_bsum.as<u32>(); ca.src = p.csr_src.as<int>();
+		ca.cap_src = p.cap_src; ca.ntot = p.ntot; ca.nrows = p.ntot + (1 << L); ca.leaf_beg = kd_beg(L); ca.sticky = a.cnt + 5;
+		const int nsb = (ca.nrows + kScanTile - 1) / kScanTile;
+		csr_count_fill_kernel<false><<<ctx->sm_count * 8, 256, 0, st>>>(ca);
+		csr_scan_sums_kernel<<<nsb, kScanBlock, 0, st>>>(ca);
+		csr_scan_top_kernel<<<1, kScanBlock, 0, st>>>(ca, nsb);
+		csr_scan_apply_kernel<<<nsb, kScanBlock, 0, st>>>(ca);
+		csr_count_fill_kernel<true><<<ctx->sm_count * 8, 256, 0, st>>>(ca);
+		csr_sort_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ca);
+		ctx->launches += 6;
+		NBCO_CUDA(cudaEventRecord(p.ev[PH_M2L], st));
+		NBCO_CUDA(cudaEventRecord(p.ev[PH_L2L], st));
+		const CsrView cv{ca.off, ca.src, p.ntot, p.cap_src};
+		ops.downward(ctx, t, spos, nullptr, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll,
+		             p.ev[PH_L2P], &cv);
+	}
+	else
+	{
 	NBCO_CUDA(cudaMemsetAsync(accn, 0, 12 * (size_t)n, st));
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_P2P], st)); // the p2p phase is exactly one kernel
 	if (c.coll)
@@ -1076,7 +1269,8 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_L2L], st));
 	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll,
-	             p.ev[PH_L2P]);
+	             p.ev[PH_L2P], nullptr);
+	}
 	if (peer) NBCO_TRY(peer_barrier(ctx)); // nobody reads this rank's centres / multipoles / positions any more
 	eval_check_kernel<<<1, 32, 0, st>>>(a.cnt, p.cap_list); LAUNCHED(ctx);
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_COUNT], st));
@@ -1146,6 +1340,13 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 		p.cap_list *= 2; p.cap_front = p.cap_list;
 		NBCO_TRY(p.p2p.reserve(8 * (size_t)p.cap_list)); NBCO_TRY(p.m2l.reserve(8 * (size_t)p.cap_list));
 		NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
+		p.cap_src = (u32)std::min<int64_t>(4ll * p.cap_list, 0x7fffffff);
+		if (p.csr_ready)
+		{
+			NBCO_TRY(p.csr_src.reserve(4 * (size_t)p.cap_src));
+			// an evaluation that overflowed may have left row counters behind: start the rows from zero again
+			NBCO_CUDA(cudaMemsetAsync(p.csr_deg.p, 0, 4 * ((size_t)p.ntot + ((size_t)1 << p.L) + 1), ctx->stream));
+		}
 		p.queue_clean = false; p.rec_valid = false;
 		if (!ctx->cfg.unsort) do_build = false;
 	}
@@ -1222,7 +1423,8 @@ void fmm3_destroy(nbco_ctx *ctx)
 	if (!ctx->fmm) return;
 	FmmPlan &p = *ctx->fmm;
 	kd_release(p.kd);
-	DevBuf *all[] = {&p.center, &p.mpole, &p.local, &p.tmp3, &p.accn, &p.p2p, &p.m2l, &p.frontA, &p.frontB, &p.cnt, &p.mfac};
+	DevBuf *all[] = {&p.center, &p.mpole, &p.local, &p.tmp3, &p.accn, &p.p2p, &p.m2l, &p.frontA, &p.frontB, &p.cnt, &p.mfac,
+	                 &p.csr_deg, &p.csr_off, &p.csr_src, &p.csr_bsum};
 	for (DevBuf *b : all) b->release();
 	if (p.ev_ok)
 		for (int k = 0; k < FmmPlan::kEvRing; ++k)

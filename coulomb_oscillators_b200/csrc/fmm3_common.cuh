@@ -146,14 +146,22 @@ __device__ __forceinline__ int owner_of(int64_t j, int64_t n, int l, unsigned lo
 	return q;
 }
 
-// intra-leaf near field of one particle (fmm_p2p3_self_kdtree, :1048-1120): the other particles of its
-// leaf, read through L1 (a leaf is 1-2 cache lines); i = j contributes exactly 0
-__device__ __forceinline__ void self_p2p(float *f, const float *__restrict__ spos, int64_t j, int leaf,
-                                         float x, float y, float z, int64_t n, int L, float eps2)
+// Interaction lists bucketed BY TARGET (round 2): one compressed-row structure over the target ids
+//   [0, ntot)            M2L: the sources of every node        (entries = source node ids)
+//   [ntot, ntot + 2^L)   P2P: the source leaves of every leaf  (entries = source leaf node ids)
+// Rows are sorted by source id, so every local expansion and every acceleration is ONE deterministic sum in registers,
+// stored once: no float atomics, no zero-fill of the locals, no near-field accumulation buffer.
+struct CsrView
 {
-	const int64_t s0 = seg_start(n, leaf, L);
-	const int cnt = (int)(seg_start(n, leaf + 1, L) - s0);
-	const float *__restrict__ lp = spos + 3 * s0; // 64-bit address once, small offsets below (the L2P kernel is issue-bound)
+	const u32 *off;   // ntot + 2^L + 1 row offsets
+	const int *src;
+	int ntot;
+	u32 cap;          // entries of src (rows are clamped to it: an evaluation that does not fit is repeated by the host)
+};
+
+// near field of one particle against the particles of one source leaf (fmm_p2p_interaction, :767-792, one direction)
+__device__ __forceinline__ void leaf_p2p(float *f, const float *__restrict__ lp, int cnt, float x, float y, float z, float eps2)
+{
 	float ax = 0.f, ay = 0.f, az = 0.f;
 	auto term = [&](int k)
 	{
@@ -171,8 +179,18 @@ __device__ __forceinline__ void self_p2p(float *f, const float *__restrict__ spo
 	for (int k = 0; k < 8; ++k)
 		if (k < cnt) term(k);
 	for (int k = 8; k < cnt; ++k) term(k);
-	(void)j;
 	f[0] += ax; f[1] += ay; f[2] += az;
+}
+
+// intra-leaf near field of one particle (fmm_p2p3_self_kdtree, :1048-1120): the other particles of its leaf, read
+// through L1 (a leaf is 1-2 cache lines); i = j contributes exactly 0
+__device__ __forceinline__ void self_p2p(float *f, const float *__restrict__ spos, int64_t j, int leaf,
+                                         float x, float y, float z, int64_t n, int L, float eps2)
+{
+	const int64_t s0 = seg_start(n, leaf, L);
+	const int cnt = (int)(seg_start(n, leaf + 1, L) - s0);
+	(void)j;
+	leaf_p2p(f, spos + 3 * s0, cnt, x, y, z, eps2);
 }
 
 // Order-specific passes (one translation unit per order: the unrolled templates are expensive
@@ -184,9 +202,14 @@ struct OrderOps
 	void (*upward)(nbco_ctx *ctx, TreeData t, const float *spos, int64_t n, int L, int r, int g, int part);
 	void (*m2l)(nbco_ctx *ctx, TreeData t, const int2 *list, const unsigned *count, unsigned cap, float eps2);
 	// rank r of 2^g ranks pushes locals down its own subtree (plus the ancestors of its root) only
+	// csr == nullptr: pair lists (M2L done by m2l(), near field summed into acc_near by the pair kernel); csr != nullptr:
+	// by-target flow: the levels gather their M2L sources themselves (no m2l() call, locals need no zero-fill) and the
+	// L2P kernel gathers the near field (acc_near unused)
 	void (*downward)(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
 	                 const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g,
-	                 float eps2, int coll, cudaEvent_t ev_l2p /* recorded between the L2L levels and the L2P kernel */);
+	                 float eps2, int coll, cudaEvent_t ev_l2p /* recorded between the L2L levels and the L2P kernel */,
+	                 const CsrView *csr);
+	int by_target;   // 1: the passes of this order implement the by-target flow
 };
 const OrderOps *order_ops(int order);
 

@@ -228,6 +228,183 @@ m2l_kernel(TreeData t, const int2 *__restrict__ list, const u32 *__restrict__ co
 }
 
 // =====================================================================================
+//  by-target downward pass (round 2): M2L gathered per TARGET node inside the L2L levels
+// =====================================================================================
+// Lq += sum over the sources row[sub], row[sub + G], ... of the target's M2L row (sorted by source id)
+template <int P>
+__device__ __forceinline__ void m2l_gather(const TreeData &t, const CsrView &csr, int node, const float4 &ct, float *Lq, int sub, int G, float eps2)
+{
+	const u32 e1 = min(csr.off[node + 1], csr.cap);
+	for (u32 e = csr.off[node] + sub; e < e1; e += G)
+	{
+		const int sn = csr.src[e];
+		const float4 cs = node_center(t, sn);
+		float dx = ct.x - cs.x, dy = ct.y - cs.y, dz = ct.z - cs.z; // c_target - c_source
+		const float r2 = dx*dx + dy*dy + dz*dz + eps2;
+		const float rinv = 1.f / sqrtf(r2); // IEEE sqrt and divide like the reference (:636-637)
+		dx *= rinv; dy *= rinv; dz *= rinv;
+		float M[pad4<sym_off(P)>()];
+		load_tuple<sym_off(P)>(M, node_mpole(t, sn));
+		m2l_weight<P>(M);
+		m2l_acc_w<P>(Lq, M, dx, dy, dz, rinv);
+	}
+}
+
+// one node of the downward pass: local = (M2L sum of its row) + (shift of the parent's local); stored once
+template <int P>
+__device__ __forceinline__ void down_node(const TreeData &t, const CsrView &csr, int child, float eps2, bool has_parent)
+{
+	const float4 cc = t.center[child];
+	float Lc[pad4<trl_off(P + 1)>()];
+#pragma unroll
+	for (int k = 0; k < pad4<trl_off(P + 1)>(); ++k) Lc[k] = 0.f;
+	m2l_gather<P>(t, csr, child, cc, Lc, 0, 1, eps2);
+	if (has_parent)
+	{
+		const int parent = (child - 1) >> 1;
+		const float4 cp = t.center[parent];
+		float Lp[pad4<trl_off(P + 1)>()], S[sym_off(P + 1)];
+		load_tuple<trl_off(P + 1)>(Lp, t.local + (int64_t)parent * t.sL);
+		S[0] = 0.f;
+		local_expand<P>(S, Lp);
+		l2l_acc<P>(Lc, S, cc.x - cp.x, cc.y - cp.y, cc.z - cp.z);
+	}
+	Lc[0] = 0.f;
+	store_tuple<trl_off(P + 1)>(t.local + (int64_t)child * t.sL, Lc);
+}
+
+template <int P>
+__global__ void __launch_bounds__(128) down_level_kernel(TreeData t, CsrView csr, int lchild, int first, int count, float eps2)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) down_node<P>(t, csr, kd_beg(lchild) + first + i, eps2, lchild >= 2);
+}
+
+// wide levels, tuples of 16 floats (P <= 3): FOUR lanes per node.  The lanes share the node's M2L row (sources sub,
+// sub + 4, ...), the partial sums are reduced by butterfly shuffles, every lane moves one float4 of the parent's tuple and
+// stores one float4 of the result (fully used sectors)
+template <int P>
+__global__ void __launch_bounds__(128) down_level4_kernel(TreeData t, CsrView csr, int lchild, int first, int count, float eps2)
+{
+	static_assert(pad4<trl_off(P + 1)>() == 16, "four float4 per tuple");
+	const int gt = blockIdx.x * blockDim.x + threadIdx.x, i = gt >> 2, sub = gt & 3;
+	if (i >= count) return; // a whole group of four leaves together
+	const unsigned gmask = 0xFu << ((threadIdx.x & 31) & ~3);
+	const int child = kd_beg(lchild) + first + i, parent = (child - 1) >> 1;
+	const float4 cc = t.center[child];
+	float Lc[16];
+#pragma unroll
+	for (int k = 0; k < 16; ++k) Lc[k] = 0.f;
+	m2l_gather<P>(t, csr, child, cc, Lc, sub, 4, eps2);
+#pragma unroll
+	for (int k = 1; k < trl_off(P + 1); ++k)
+	{
+		Lc[k] += __shfl_xor_sync(gmask, Lc[k], 1, 4);
+		Lc[k] += __shfl_xor_sync(gmask, Lc[k], 2, 4);
+	}
+	if (lchild >= 2)
+	{
+		const float4 qp = reinterpret_cast<const float4 *>(t.local + (int64_t)parent * t.sL)[sub];
+		const float4 cp = t.center[parent];
+		float Lp[16], S[sym_off(P + 1)];
+#pragma unroll
+		for (int q = 0; q < 4; ++q)
+		{
+			Lp[4*q]   = __shfl_sync(gmask, qp.x, q, 4); Lp[4*q+1] = __shfl_sync(gmask, qp.y, q, 4);
+			Lp[4*q+2] = __shfl_sync(gmask, qp.z, q, 4); Lp[4*q+3] = __shfl_sync(gmask, qp.w, q, 4);
+		}
+		S[0] = 0.f;
+		local_expand<P>(S, Lp);
+		l2l_acc<P>(Lc, S, cc.x - cp.x, cc.y - cp.y, cc.z - cp.z);
+	}
+	Lc[0] = 0.f;
+	float4 out;
+	out.x = sub == 0 ? Lc[0] : (sub == 1 ? Lc[4] : (sub == 2 ? Lc[8]  : Lc[12]));
+	out.y = sub == 0 ? Lc[1] : (sub == 1 ? Lc[5] : (sub == 2 ? Lc[9]  : Lc[13]));
+	out.z = sub == 0 ? Lc[2] : (sub == 1 ? Lc[6] : (sub == 2 ? Lc[10] : Lc[14]));
+	out.w = sub == 0 ? Lc[3] : (sub == 1 ? Lc[7] : (sub == 2 ? Lc[11] : Lc[15]));
+	reinterpret_cast<float4 *>(t.local + (int64_t)child * t.sL)[sub] = out;
+}
+
+// child levels lfirst .. llast of the subtree under node (lfirst - 1, first + blockIdx.x), one CTA per subtree
+template <int P>
+__global__ void __launch_bounds__(128) down_sub_kernel(TreeData t, CsrView csr, int lfirst, int llast, int first, float eps2)
+{
+	const int root = first + blockIdx.x, lroot = lfirst - 1;
+	for (int l = lfirst; l <= llast; ++l)
+	{
+		const int cnt = 1 << (l - lroot), f = root << (l - lroot);
+		for (int i = threadIdx.x; i < cnt; i += blockDim.x)
+			down_node<P>(t, csr, kd_beg(l) + f + i, eps2, l >= 2);
+		__syncthreads();
+	}
+}
+
+// levels 0 .. llast in one CTA (levels 0 and 1 have empty rows and no parent: their locals become zero)
+template <int P>
+__global__ void __launch_bounds__(256) down_top_kernel(TreeData t, CsrView csr, int llast, float eps2)
+{
+	for (int l = 0; l <= llast; ++l)
+	{
+		for (int i = threadIdx.x; i < (1 << l); i += blockDim.x)
+			down_node<P>(t, csr, kd_beg(l) + i, eps2, l >= 2);
+		__syncthreads();
+	}
+}
+
+// L2P + near field gathered per TARGET leaf (own leaf + the leaves of its P2P row) + rescale + optional elastic term +
+// optional un-sort, one pass over the particles: every acceleration is one sum in registers, stored once
+template <int P>
+__global__ void __launch_bounds__(128)
+l2p_near_kernel(TreeData t, CsrView csr, const float *__restrict__ spos, float *__restrict__ acc_out,
+                const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int64_t n, int L, int64_t j_lo, int64_t j_hi, float eps2, int coll)
+{
+	const float scale = param ? param[0] : 1.f;
+	float k3[3] = {1.f, 1.f, 1.f};
+	if (fuse_elastic && param) { k3[0] = param[3]; k3[1] = param[4]; k3[2] = param[5]; }
+	const int beg = kd_beg(L);
+	const unsigned long long magic = ~0ull / (unsigned long long)n;
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t j = j_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < j_hi; j += stride)
+	{
+		const int leaf = owner_of(j, n, L, magic);
+		const float4 c = t.center[beg + leaf];
+		float Lq[pad4<trl_off(P + 1)>()], S[sym_off(P + 1)];
+		load_tuple<trl_off(P + 1)>(Lq, t.local + (int64_t)(beg + leaf) * t.sL);
+		S[0] = 0.f;
+		local_expand<P>(S, Lq);
+		const float x = spos[3*j], y = spos[3*j+1], z = spos[3*j+2];
+		float f[3];
+		l2p_field<P>(f, S, x - c.x, y - c.y, z - c.z);
+		if (coll)
+		{
+			float fn[3] = {0.f, 0.f, 0.f};
+			self_p2p(fn, spos, j, leaf, x, y, z, n, L, eps2);
+			const u32 e1 = min(csr.off[csr.ntot + leaf + 1], csr.cap);
+			for (u32 e = csr.off[csr.ntot + leaf]; e < e1; ++e)
+			{
+				const int sl = csr.src[e] - beg;
+				const int64_t s0 = seg_start(n, sl, L);
+				const int cnt = (int)(seg_start(n, sl + 1, L) - s0);
+				// multi-GPU: the particles of a remote source leaf are read from their owner's published positions
+				const float *__restrict__ sp = spos;
+				if (t.peers.g > 0)
+				{
+					const int o = sl >> (L - t.peers.g);
+					if (o != t.peers.me) sp = t.peers.pos[o];
+				}
+				leaf_p2p(fn, sp + 3 * s0, cnt, x, y, z, eps2);
+			}
+			f[0] += fn[0]; f[1] += fn[1]; f[2] += fn[2];
+		}
+		float ax = f[0] * scale, ay = f[1] * scale, az = f[2] * scale;
+		if (fuse_elastic) { ax = fmaf(-k3[0], x, ax); ay = fmaf(-k3[1], y, ay); az = fmaf(-k3[2], z, az); }
+		const int64_t o = perm_or_null ? (int64_t)perm_or_null[j] : j;
+		acc_out[3*o] = ax; acc_out[3*o+1] = ay; acc_out[3*o+2] = az;
+	}
+}
+
+// =====================================================================================
 //  downward pass (replaces fmm_pushl3_kdtree*, fmm_pushLeaves3_kdtree*, rescale, add_elastic)
 // =====================================================================================
 template <int P>
@@ -389,9 +566,45 @@ struct OrderImpl
 	{
 		m2l_kernel<P><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2); ++ctx->launches;
 	}
-	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p)
+	// by-target flow: same level schedule as below (top levels in one CTA, chunks of kSubLevels levels per subtree CTA
+	// while a level is small, one launch per wide level), every node gathers its own M2L row
+	static void downward_by_target(nbco_ctx *ctx, TreeData t, const float *spos, float *acc_out, const int *perm_or_null, const float *param,
+	                               int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p, const CsrView &csr)
 	{
+		cudaStream_t st = ctx->stream;
+		const int ltop = std::min(L, kTopLevels + 1);
+		down_top_kernel<P><<<1, 256, 0, st>>>(t, csr, ltop, eps2); ++ctx->launches;
+		int lf = kTopLevels + 2;
+		for (; lf <= L; lf += kSubLevels)
+		{
+			int ll = std::min(lf + kSubLevels - 1, L);
+			while (ll >= lf && ll >= g && (1 << (ll - g)) >= kWideLevel) --ll; // leave the wide levels to the loop below
+			if (ll < lf) break;
+			const int lroot = lf - 1;
+			const int first = lroot >= g ? r << (lroot - g) : r >> (g - lroot), count = lroot >= g ? 1 << (lroot - g) : 1;
+			down_sub_kernel<P><<<count, 128, 0, st>>>(t, csr, lf, ll, first, eps2); ++ctx->launches;
+			if (ll < lf + kSubLevels - 1) { lf = ll + 1; break; }
+		}
+		for (int l = lf; l <= L; ++l)
+		{
+			const int first = l >= g ? r << (l - g) : r >> (g - l), count = l >= g ? 1 << (l - g) : 1;
+			if constexpr (pad4<trl_off(P + 1)>() == 16)
+				down_level4_kernel<P><<<(4 * count + 127) / 128, 128, 0, st>>>(t, csr, l, first, count, eps2);
+			else
+				down_level_kernel<P><<<(count + 127) / 128, 128, 0, st>>>(t, csr, l, first, count, eps2);
+			++ctx->launches;
+		}
+		if (ev_l2p) cudaEventRecord(ev_l2p, st);
+		const int64_t j_lo = seg_start(n, r, g), j_hi = seg_start(n, r + 1, g);
+		l2p_near_kernel<P><<<grid_for(j_hi - j_lo, 128, ctx->sm_count, 16), 128, 0, st>>>(t, csr, spos, acc_out, perm_or_null, param, fuse_elastic,
+		                                                                                   n, L, j_lo, j_hi, eps2, coll);
+		++ctx->launches;
+	}
+	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
+	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p,
+	                     const CsrView *csr)
+	{
+		if (csr) { downward_by_target(ctx, t, spos, acc_out, perm_or_null, param, fuse_elastic, n, L, r, g, eps2, coll, ev_l2p, *csr); return; }
 		cudaStream_t st = ctx->stream;
 		// locals of levels 0 and 1 stay zero (nothing is ever admissible there); level l+1 pulls from level l >= 1
 		if (L >= 2)
@@ -432,6 +645,6 @@ struct OrderImpl
 
 #define NBCO_INSTANTIATE_ORDER(P)                                                                          \
 	extern const OrderOps kOrderOps##P;                                                                    \
-	const OrderOps kOrderOps##P = {OrderImpl<P>::upward, OrderImpl<P>::m2l, OrderImpl<P>::downward};
+	const OrderOps kOrderOps##P = {OrderImpl<P>::upward, OrderImpl<P>::m2l, OrderImpl<P>::downward, 1};
 
 } // namespace nbco

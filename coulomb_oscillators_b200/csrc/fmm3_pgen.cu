@@ -353,7 +353,8 @@ struct GenImpl
 		g_m2l_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2, P); ++ctx->launches;
 	}
 	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
-	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p)
+	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p,
+	                     const CsrView *)
 	{
 		cudaStream_t st = ctx->stream;
 		if (L >= 2)
@@ -377,7 +378,7 @@ struct GenImpl
 
 #define NBCO_GENERIC_ORDER(P) \
 	extern const OrderOps kOrderOps##P; \
-	const OrderOps kOrderOps##P = {GenImpl<P>::upward, GenImpl<P>::m2l, GenImpl<P>::downward};
+	const OrderOps kOrderOps##P = {GenImpl<P>::upward, GenImpl<P>::m2l, GenImpl<P>::downward, 0};
 
 #ifndef NBCO_STATIC_ORDER_MAX
 #define NBCO_STATIC_ORDER_MAX 5

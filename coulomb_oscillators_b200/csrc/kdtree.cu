@@ -406,14 +406,17 @@ top_resolve_kernel(float4 *__restrict__ out, float4 *__restrict__ scratch, TreeG
 constexpr int kMaxHistBlk = 128;     // histogram mode: blocks of >= 64 slots (at most kBottomCap / 64 of them)
 constexpr u16 kNoSlot = 0xffffu;
 
+struct BlkBox { float lb[3], rb[3]; int chain, axis; }; // box of a block's node, its tie-break chain and split axis
+
 struct BottomSmem
 {
 	float *c;            // [3][kBottomCap] coordinates by slot
 	u16 *ordA, *ordB;    // slot permutation, ping-pong; kNoSlot pads every block to its power-of-two size
 	u32 *ckey;           // keys (ordered bits) parallel to a candidate list / to the block positions
 	u32 *hist;           // [blocks][bins], at most kBottomCap / 8 counters
+	BlkBox *box[2];      // histogram levels: boxes of the blocks of this level / of the next one (no global round trip)
 	// per-block state of a histogram level
-	int *b_axis, *b_chain, *b_cnt, *b_kl;
+	int *b_kl;
 	float *b_lo, *b_scale;
 	u32 *b_pb, *b_less, *b_eq, *b_curL, *b_curE, *b_curR, *b_rmin, *b_cutL, *b_cutR;
 };
@@ -431,6 +434,18 @@ __device__ __forceinline__ bool slot_tie_less(const BottomSmem &s, u32 sa, u32 s
 	return __float_as_uint(pay0[sa].w) < __float_as_uint(pay0[sb].w);
 }
 
+// write_box (fmm3_common.cuh) that also returns the node's state for the next level
+__device__ __forceinline__ void write_box_keep(const TreeGeom &g, int node, const float *lb, const float *rb, int parent_chain, BlkBox *keep)
+{
+	write_box(g, node, lb, rb, parent_chain);
+	if (keep)
+	{
+		const int ax = widest_axis(rb[0] - lb[0], rb[1] - lb[1], rb[2] - lb[2]);
+		for (int k = 0; k < 3; ++k) { keep->lb[k] = lb[k]; keep->rb[k] = rb[k]; }
+		keep->axis = ax; keep->chain = chain_push(ax, parent_chain);
+	}
+}
+
 __global__ void __launch_bounds__(kBottomThreads, 1)
 kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__ spos, int *__restrict__ perm,
                  int64_t n, int lt, int L, int P2, int blk0)
@@ -444,8 +459,10 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 		s.hist = reinterpret_cast<u32 *>(p); p += sizeof(u32) * (kBottomCap / 8);
 		s.ordA = reinterpret_cast<u16 *>(p); p += sizeof(u16) * kBottomCap;
 		s.ordB = reinterpret_cast<u16 *>(p); p += sizeof(u16) * kBottomCap;
+		s.box[0] = reinterpret_cast<BlkBox *>(p); p += sizeof(BlkBox) * kMaxHistBlk;
+		s.box[1] = reinterpret_cast<BlkBox *>(p); p += sizeof(BlkBox) * kMaxHistBlk;
 		int *q = reinterpret_cast<int *>(p);
-		s.b_axis = q; q += kMaxHistBlk; s.b_chain = q; q += kMaxHistBlk; s.b_cnt = q; q += kMaxHistBlk; s.b_kl = q; q += kMaxHistBlk;
+		s.b_kl = q; q += kMaxHistBlk;
 		s.b_lo = reinterpret_cast<float *>(q); q += kMaxHistBlk; s.b_scale = reinterpret_cast<float *>(q); q += kMaxHistBlk;
 		u32 *u = reinterpret_cast<u32 *>(q);
 		s.b_pb = u; u += kMaxHistBlk; s.b_less = u; u += kMaxHistBlk; s.b_eq = u; u += kMaxHistBlk;
@@ -459,15 +476,31 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 	const float4 *__restrict__ pay0 = pay + s0;
 	constexpr int kPer = kBottomCap / kBottomThreads;
 
-	for (int t = tid; t < c0; t += kBottomThreads)
 	{
-		const float4 p = pay0[t];
-		s.c[t] = p.x; s.c[kBottomCap + t] = p.y; s.c[2 * kBottomCap + t] = p.z;
+		// all loads of a thread are issued before the first store (one memory round trip, not eight)
+		float4 v[kPer];
+#pragma unroll
+		for (int e = 0; e < kPer; ++e) { const int t = tid + e * kBottomThreads; v[e] = t < c0 ? pay0[t] : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+		for (int e = 0; e < kPer; ++e)
+		{
+			const int t = tid + e * kBottomThreads;
+			if (t < c0) { s.c[t] = v[e].x; s.c[kBottomCap + t] = v[e].y; s.c[2 * kBottomCap + t] = v[e].z; }
+		}
 	}
 	for (int p = tid; p < P2; p += kBottomThreads) s.ordA[p] = p < c0 ? (u16)p : kNoSlot;
+	if (tid == 0)
+	{
+		const int node = kd_beg(lt) + b;
+		BlkBox bx;
+		for (int k = 0; k < 3; ++k) { bx.lb[k] = g.lbound[3*node+k]; bx.rb[k] = g.rbound[3*node+k]; }
+		bx.axis = g.splitdim[node]; bx.chain = g.chain[node];
+		s.box[0][0] = bx;
+	}
 	__syncthreads();
 
 	u16 *oin = s.ordA, *oout = s.ordB;
+	int cb = 0; // s.box[cb] holds the boxes of the current level's blocks while the levels run in histogram mode
 	const int nlev = L - lt; // levels lt .. L-1 are split here
 	for (int j = 0; j < nlev; ++j)
 	{
@@ -482,15 +515,15 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 		{
 			// ================= histogram mode =================
 			const int nb = min(256, B >> 3);
+			const BlkBox *bx = s.box[cb];
+			BlkBox *bnext = 2 * nblk <= kMaxHistBlk ? s.box[cb ^ 1] : nullptr;
 			if (tid < nblk)
 			{
 				const int64_t i = i0 + tid;
-				const int node = node0 + tid, axis = g.splitdim[node];
-				s.b_axis[tid] = axis; s.b_chain[tid] = g.chain[node];
-				s.b_cnt[tid] = (int)(seg_start(n, i + 1, l) - seg_start(n, i, l));
+				const int axis = bx[tid].axis;
 				s.b_kl[tid] = (int)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
-				const float lo = g.lbound[3*node + axis];
-				s.b_lo[tid] = lo; s.b_scale[tid] = bin_scale(lo, g.rbound[3*node + axis], nb);
+				const float lo = bx[tid].lb[axis];
+				s.b_lo[tid] = lo; s.b_scale[tid] = bin_scale(lo, bx[tid].rb[axis], nb);
 				s.b_curL[tid] = s.b_curE[tid] = s.b_curR[tid] = 0;
 				s.b_rmin[tid] = s.b_cutL[tid] = s.b_cutR[tid] = 0xffffffffu;
 			}
@@ -509,27 +542,35 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 					if (slot != kNoSlot)
 					{
 						const int q = p >> logB;
-						const int bin = bin_of(s.c[s.b_axis[q] * kBottomCap + slot], s.b_lo[q], s.b_scale[q], nb);
+						const int bin = bin_of(s.c[bx[q].axis * kBottomCap + slot], s.b_lo[q], s.b_scale[q], nb);
 						atomicAdd(&s.hist[q * nb + bin], 1u);
 						sb[e] = slot | ((u32)bin << 16);
 					}
 				}
 			}
 			__syncthreads();
-			// (2) pivot bin of every block
-			if (tid < nblk)
+			// (2) pivot bin of every block: a warp scans the (at most 256) bins of a block
+			for (int q = warp; q < nblk; q += kBottomThreads / 32)
 			{
-				const u32 *h = s.hist + tid * nb;
-				const u32 krank = (u32)s.b_kl[tid] - 1u;
-				u32 run = 0;
-				int pb = 0;
-				for (; pb < nb - 1; ++pb)
+				const u32 *h = s.hist + q * nb;
+				const u32 krank = (u32)s.b_kl[q] - 1u;
+				const int per = (nb + 31) >> 5; // bins per lane (1 .. 8), lane-contiguous
+				u32 c[8], sum = 0;
+#pragma unroll
+				for (int k = 0; k < 8; ++k) { const int bi = lane * per + k; c[k] = (k < per && bi < nb) ? h[bi] : 0u; sum += c[k]; }
+				u32 incl = sum;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+				u32 run = incl - sum;
+				if (krank >= run && krank < run + sum)
 				{
-					const u32 c = h[pb];
-					if (krank < run + c) break;
-					run += c;
+#pragma unroll
+					for (int k = 0; k < 8; ++k)
+					{
+						if (k < per && krank >= run && krank < run + c[k]) { s.b_pb[q] = (u32)(lane * per + k); s.b_less[q] = run; s.b_eq[q] = c[k]; }
+						run += c[k];
+					}
 				}
-				s.b_pb[tid] = (u32)pb; s.b_less[tid] = run; s.b_eq[tid] = h[pb];
 			}
 			__syncthreads();
 			// (3) three-way split: the 32 positions of a warp lie in one block (B >= 64)
@@ -553,9 +594,12 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 				ol = __shfl_sync(0xffffffffu, ol, 0); oe = __shfl_sync(0xffffffffu, oe, 0); orr = __shfl_sync(0xffffffffu, orr, 0);
 				const u32 lt_mask = (1u << lane) - 1u;
 				u32 key = 0xffffffffu;
-				if (ise || isr) key = ordered_bits(s.c[s.b_axis[q] * kBottomCap + slot]);
-				const u32 rmin = __reduce_min_sync(0xffffffffu, isr ? key : 0xffffffffu);
-				if (lane == 0 && br) atomicMin(&s.b_rmin[q], rmin);
+				if (ise || isr) key = ordered_bits(s.c[bx[q].axis * kBottomCap + slot]);
+				if (br)
+				{
+					const u32 rmin = __reduce_min_sync(0xffffffffu, isr ? key : 0xffffffffu);
+					if (lane == 0) atomicMin(&s.b_rmin[q], rmin);
+				}
 				const int qB = q << logB;
 				if (isl) oout[qB + ol + __popc(bl & lt_mask)] = (u16)slot;
 				else if (isr) oout[qB + (B >> 1) + (eq - need) + orr + __popc(br & lt_mask)] = (u16)slot;
@@ -574,18 +618,21 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 				for (int q = warp / wpb; q < nblk; q += ngroups)
 				{
 					const u32 less = s.b_less[q], eq = s.b_eq[q], need = (u32)s.b_kl[q] - less;
-					const int cb = (q << logB) + (int)less, chain = s.b_chain[q];
+					const int cbase = (q << logB) + (int)less, chain = bx[q].chain;
 					for (u32 c = gl; c < eq; c += gstride)
 					{
-						const u32 kc = s.ckey[cb + c], sc = oin[cb + c];
-						u32 rank = 0;
+						const u32 kc = s.ckey[cbase + c], sc = oin[cbase + c];
+						u32 rank = 0, ties = 0;
 						for (u32 f = 0; f < eq; ++f)
 						{
-							const u32 kf = s.ckey[cb + f];
-							if (kf < kc) ++rank;
-							else if (kf == kc && f != c && slot_tie_less(s, oin[cb + f], sc, chain, pay0)) ++rank;
+							const u32 kf = s.ckey[cbase + f];
+							rank += kf < kc ? 1u : 0u;
+							ties += kf == kc ? 1u : 0u;
 						}
-						if (rank < need) oout[cb + rank] = (u16)sc;
+						if (ties > 1u) // equal keys (rare): the rest of the total order decides
+							for (u32 f = 0; f < eq; ++f)
+								if (f != c && s.ckey[cbase + f] == kc && slot_tie_less(s, oin[cbase + f], sc, chain, pay0)) ++rank;
+						if (rank < need) oout[cbase + rank] = (u16)sc;
 						else oout[(q << logB) + (B >> 1) + (rank - need)] = (u16)sc;
 						if (rank == need - 1) s.b_cutL[q] = kc;
 						if (rank == need) s.b_cutR[q] = kc;
@@ -593,61 +640,86 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 				}
 			}
 			__syncthreads();
-			// (5) boxes of the children (evalBox_krnl for level l+1)
+			// (5) boxes of the children (evalBox_krnl for level l+1); kept in shared memory for the next histogram level
 			if (tid < nblk)
 			{
-				const int node = node0 + tid, axis = s.b_axis[tid], pch = s.b_chain[tid];
+				const int node = node0 + tid, axis = bx[tid].axis, pch = bx[tid].chain;
 				float lb[3], rb[3];
-				for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
+				for (int k = 0; k < 3; ++k) { lb[k] = bx[tid].lb[k]; rb[k] = bx[tid].rb[k]; }
 				const float save = rb[axis];
 				rb[axis] = unordered_bits(s.b_cutL[tid]);
-				write_box(g, 2*node + 1, lb, rb, pch);
+				write_box_keep(g, 2*node + 1, lb, rb, pch, bnext ? bnext + 2 * tid : nullptr);
 				rb[axis] = save;
 				lb[axis] = unordered_bits(min(s.b_cutR[tid], s.b_rmin[tid]));
-				write_box(g, 2*node + 2, lb, rb, pch);
+				write_box_keep(g, 2*node + 2, lb, rb, pch, bnext ? bnext + 2 * tid + 1 : nullptr);
 			}
+			cb ^= 1;
 		}
 		else
 		{
 			// ================= ranking mode: blocks of <= 32 slots, and the last level (a true sort) =================
+			// (a) keys by position; the pads of a block get the largest key, so that a block is scanned without bounds
 			for (int p = tid; p < P2; p += kBottomThreads)
 			{
 				const u32 slot = oin[p];
-				if (slot != kNoSlot) s.ckey[p] = ordered_bits(s.c[g.splitdim[node0 + (p >> logB)] * kBottomCap + slot]);
+				s.ckey[p] = slot != kNoSlot ? ordered_bits(s.c[g.splitdim[node0 + (p >> logB)] * kBottomCap + slot]) : 0xffffffffu;
 			}
 			__syncthreads();
+			// (b) rank by counting smaller keys of the block; equal keys (rare) take the slow path
 			for (int p = tid; p < P2; p += kBottomThreads)
 			{
 				const u32 slot = oin[p];
 				if (slot == kNoSlot) continue;
-				const int q = p >> logB, qB = q << logB, node = node0 + q;
-				const int64_t i = i0 + q;
-				const int cnt = (int)(seg_start(n, i + 1, l) - seg_start(n, i, l));
-				const int kl = (int)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
+				const int q = p >> logB, qB = q << logB;
 				const u32 kc = s.ckey[p];
-				int chain = -1;
-				int rank = 0;
-				for (int f = 0; f < cnt; ++f)
+				u32 rank = 0, ties = 0;
+				if (B >= 4)
 				{
-					const u32 kf = s.ckey[qB + f];
-					if (kf < kc) ++rank;
-					else if (kf == kc && qB + f != p)
+					const uint4 *kv = reinterpret_cast<const uint4 *>(s.ckey + qB);
+					for (int f = 0; f < (B >> 2); ++f)
 					{
-						if (chain < 0) chain = g.chain[node];
-						if (slot_tie_less(s, oin[qB + f], slot, chain, pay0)) ++rank;
+						const uint4 k4 = kv[f];
+						rank += (k4.x < kc ? 1u : 0u) + (k4.y < kc ? 1u : 0u) + (k4.z < kc ? 1u : 0u) + (k4.w < kc ? 1u : 0u);
+						ties += (k4.x == kc ? 1u : 0u) + (k4.y == kc ? 1u : 0u) + (k4.z == kc ? 1u : 0u) + (k4.w == kc ? 1u : 0u);
 					}
 				}
-				oout[last ? qB + rank : (rank < kl ? qB + rank : qB + (B >> 1) + (rank - kl))] = (u16)slot;
-				if (rank == kl - 1 || rank == kl)
+				else
+					for (int f = 0; f < B; ++f) { const u32 kf = s.ckey[qB + f]; rank += kf < kc ? 1u : 0u; ties += kf == kc ? 1u : 0u; }
+				if (ties > 1u)
 				{
-					// this particle bounds a child: left child's last (rank kl-1) or right child's first (rank kl)
-					const int axis = g.splitdim[node], pch = g.chain[node];
-					float lb[3], rb[3];
-					for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
-					const float x = s.c[axis * kBottomCap + slot];
-					if (rank == kl - 1) { rb[axis] = x; write_box(g, 2*node + 1, lb, rb, pch); }
-					else { lb[axis] = x; write_box(g, 2*node + 2, lb, rb, pch); }
+					const int chain = g.chain[node0 + q];
+					for (int f = 0; f < B; ++f)
+					{
+						const u32 sf = oin[qB + f];
+						if (qB + f != p && sf != kNoSlot && s.ckey[qB + f] == kc && slot_tie_less(s, sf, slot, chain, pay0)) ++rank;
+					}
 				}
+				int dst = qB + (int)rank;
+				if (!last)
+				{
+					const int64_t i = i0 + q;
+					const int kl = (int)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
+					if ((int)rank >= kl) dst = qB + (B >> 1) + ((int)rank - kl);
+				}
+				oout[dst] = (u16)slot;
+			}
+			__syncthreads();
+			// (c) boxes of the children: the particles of rank kl-1 and kl sit at known positions of the output
+			for (int q = tid; q < nblk; q += kBottomThreads)
+			{
+				const int64_t i = i0 + q;
+				const int node = node0 + q, qB = q << logB;
+				const int kl = (int)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
+				const int axis = g.splitdim[node], pch = g.chain[node];
+				float lb[3], rb[3];
+				for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
+				const float cl = s.c[axis * kBottomCap + oout[qB + kl - 1]];
+				const float cr = s.c[axis * kBottomCap + oout[last ? qB + kl : qB + (B >> 1)]];
+				const float save = rb[axis];
+				rb[axis] = cl;
+				write_box(g, 2*node + 1, lb, rb, pch);
+				rb[axis] = save; lb[axis] = cr;
+				write_box(g, 2*node + 2, lb, rb, pch);
 			}
 		}
 		__syncthreads();
@@ -670,7 +742,7 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 }
 
 constexpr size_t kBottomSmemBytes = sizeof(float) * 3 * kBottomCap + sizeof(u32) * kBottomCap + sizeof(u32) * (kBottomCap / 8)
-                                    + 2 * sizeof(u16) * kBottomCap + 15 * 4 * kMaxHistBlk;
+                                    + 2 * sizeof(u16) * kBottomCap + 2 * sizeof(BlkBox) * kMaxHistBlk + 12 * 4 * kMaxHistBlk;
 
 } // namespace
 

@@ -20,6 +20,9 @@
 #include <iostream>
 #include <string>
 #include <vector>
+#include <thread>
+#include <barrier>
+#include <atomic>
 
 namespace {
 
@@ -42,7 +45,7 @@ const char *kHelp =
 	"  -iters <n>             number of iterations (n+1 steps are done). Default is 30000\n"
 	"  -steps <n>             iterations between two snapshots. Default is 200\n"
 	"  -integ <eu|fr|pefrl>   symplectic Euler, Forest-Ruth or PEFRL. Default is leapfrog\n"
-	"  -p <order>             FMM order (1..6). Default is 3\n"
+	"  -p <order>             FMM order (1..10). Default is 3\n"
 	"  -r <radius>            multipole acceptance parameter. Default is 1\n"
 	"  -eps <eps>             softening length. Default is 1e-9\n"
 	"  -i <x>                 density inhomogeneity factor for the tree depth. Default is 1\n"
@@ -50,8 +53,10 @@ const char *kHelp =
 	"  -ncoll                 skip the near field (P2P)\n"
 	"  -tree-steps <k>        (extension) rebuild the kd-tree every k force evaluations. Default is 8\n"
 	"  -m2l-first <0|1>       (extension) 1: MAC before leaf test (reference GPU order, default), 0: reference CPU order\n"
+	"  -gpus <g>              (extension) partition the kd-tree over g GPUs of this node (1, 2, 4 or 8; NVLink peer memory)\n"
+	"  -reproducible          (extension) interaction lists bucketed by target: bit-reproducible forces, no float atomics\n"
 	"  -accuracy <v>          search (p, r) for a mean relative error below v, then run\n"
-	"  -test                  timing and error against the direct sum for p = 1..6 on a uniform cube\n"
+	"  -test                  timing and error against the direct sum for p = 1..10 on a uniform cube\n"
 	"  -test2                 error against the direct sum over tree_steps+1 Euler steps\n"
 	"  -xi <v>                perveance-like coupling. Default is 2e-6\n"
 	"  -omega0 <x> <y>        transverse oscillator frequencies (z stays 1)\n"
@@ -65,6 +70,86 @@ struct Device
 	~Device() { if (buf) cudaFree(buf); if (par) cudaFree(par); if (tmp) cudaFree(tmp); if (ctx) nbco_destroy(ctx); }
 };
 
+// The main loop of main3.cu:835-858 over g GPUs of one node: one host thread and one context per GPU, rank r owns the
+// subtree of kd node (log2 g, r) (csrc/peer.cu).  The contexts live in one process, so they are
+// wired with nbco_peer_attach_local (no CUDA IPC); every rank holds its own copy of the state buffer, steps its own
+// range and the ranks meet inside the evaluator.  Snapshots: nbco_peer_gather, rank 0 writes the file.
+int run_multi_gpu(int gpus, nbco_config cfg, int scheme, std::vector<float> &host, int64_t n, const float *par6, float dt,
+                  long nIters, long nSteps, const std::string &strout)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < gpus) return fail("Error: -gpus " + std::to_string(gpus) + " but " + std::to_string(ndev) + " CUDA devices are visible.");
+	if (gpus > 8 || (gpus & (gpus - 1))) return fail("Error: -gpus must be 1, 2, 4 or 8.");
+	const size_t vb = sizeof(float) * 3 * (size_t)n;
+	std::vector<Device> dev(gpus);
+	std::barrier sync(gpus);
+	std::atomic<int> failed{0};
+	std::vector<std::string> errs(gpus);
+	auto rank_main = [&](int r)
+	{
+		auto bail = [&](const std::string &m) { errs[r] = m; failed.store(1); };
+#define RK(call) do { if (!failed.load() && (call) != NBCO_OK) bail(nbco_last_error()); } while (0)
+#define RU(call) do { if (!failed.load()) { cudaError_t e_ = (call); if (e_ != cudaSuccess) bail(std::string("GPUassert: ") + cudaGetErrorString(e_)); } } while (0)
+		Device &d = dev[r];
+		nbco_config c = cfg;
+		c.device = r; c.rank = r; c.world = gpus; c.unsort = 0;
+		RU(cudaSetDevice(r));
+		RK(nbco_create(&c, &d.ctx));
+		RU(cudaMalloc(&d.buf, 3 * vb));
+		RU(cudaMalloc(&d.par, 6 * sizeof(float)));
+		RU(cudaMemcpy(d.buf, host.data(), 2 * vb, cudaMemcpyHostToDevice));
+		RU(cudaMemcpy(d.par, par6, 6 * sizeof(float), cudaMemcpyHostToDevice));
+		unsigned char handles[192];
+		RK(nbco_peer_export(d.ctx, n, handles));
+		sync.arrive_and_wait();
+		for (int q = 0; q < gpus && !failed.load(); ++q)
+			if (q != r) RK(nbco_peer_attach_local(d.ctx, q, dev[q].ctx));
+		RK(nbco_peer_commit(d.ctx));
+		sync.arrive_and_wait();
+		if (failed.load()) return; // every rank sees the flag after the barrier: nobody enters a collective call alone
+		RK(nbco_compute_force(d.ctx, NBCO_EVAL_COULOMB_FMM3_KD, d.buf, n, d.par));
+		long iter = 0;
+		while (iter < nIters)
+		{
+			sync.arrive_and_wait();
+			if (failed.load()) return;
+			const long next = (iter % nSteps == 0) ? iter : (iter / nSteps + 1) * nSteps;
+			const long todo = std::min(next, nIters - 1) - iter + 1;
+			RK(nbco_integrate(d.ctx, scheme, NBCO_EVAL_COULOMB_FMM3_KD, d.buf, n, d.par, dt, todo));
+			iter += todo;
+			if ((iter - 1) % nSteps == 0)
+			{
+				sync.arrive_and_wait();
+				if (failed.load()) return;
+				RK(nbco_peer_gather(d.ctx, d.buf, n));
+				if (r == 0 && !failed.load())
+				{
+					std::cout << (iter - 1) << ' ' << std::flush;
+					RU(cudaMemcpy(host.data(), d.buf, 2 * vb, cudaMemcpyDeviceToHost));
+					const std::string name = strout + "/out" + std::to_string(iter - 1) + '_' + std::to_string(dt) + ".bin";
+					if (!failed.load() && nbco_state_write(name.c_str(), host.data(), n) != NBCO_OK)
+						bail("Error: cannot write on output location. Check that \"" + strout + "\" folder exists. Create it if not.");
+				}
+			}
+		}
+		sync.arrive_and_wait();
+		if (d.ctx) nbco_peer_detach(d.ctx);
+		sync.arrive_and_wait(); // every rank has closed its view of the others before anybody frees (Device destructors)
+#undef RK
+#undef RU
+	};
+	std::vector<std::thread> th;
+	for (int r = 0; r < gpus; ++r) th.emplace_back(rank_main, r);
+	for (auto &t : th) t.join();
+	std::cout << std::endl;
+	if (failed.load())
+	{
+		for (const auto &e : errs) if (!e.empty()) std::cerr << e << std::endl;
+		return -1;
+	}
+	return 0;
+}
+
 } // namespace
 
 int main(int argc, const char **argv)
@@ -76,6 +161,7 @@ int main(int argc, const char **argv)
 	long nIters = 30001, nSteps = 200;
 	std::string strout("out"), strin;
 	bool in = false, test = false, test2 = false, b_accuracy = false;
+	int gpus = 1;
 	float accuracy = 0.001f, xi = 2.e-6f;
 	float omega0[3] = {1.095f, 1.0f, 1.0f}, x[3] = {0.003f, 0.001f, 0.01f}, u[3];
 	for (int k = 0; k < 3; ++k) u[k] = omega0[k] * x[k]; // computed before parsing like main3.cu:241-245
@@ -113,6 +199,8 @@ int main(int argc, const char **argv)
 		// extensions (not in the reference CLI): its global tree_steps (constants.cuh:45) and the traversal order
 		else if (a == "-tree-steps") { if (!need(i, 1)) return fail("Error: no tree_steps specified."); cfg.tree_steps = atoi(argv[++i]); }
 		else if (a == "-m2l-first") { if (!need(i, 1)) return fail("Error: no value specified."); cfg.m2l_first = atoi(argv[++i]); }
+		else if (a == "-gpus") { if (!need(i, 1)) return fail("Error: no number of GPUs specified."); gpus = atoi(argv[++i]); if (gpus < 1) return fail("Error: invalid argument to '-gpus'"); }
+		else if (a == "-reproducible") cfg.reproducible = 1;
 		else if (a == "-accuracy") { if (!need(i, 1)) return fail("Error: no accuracy specified."); accuracy = (float)atof(argv[++i]); b_accuracy = true; }
 		else if (a == "-test") test = true;
 		else if (a == "-test2") test2 = true;
@@ -151,6 +239,12 @@ int main(int argc, const char **argv)
 		for (int i = 0; i < argc; ++i) farg << argv[i] << ' ';
 	}
 	const float par[6] = {xi / (float)nBodies, 0, 0, omega0[0] * omega0[0], omega0[1] * omega0[1], omega0[2] * omega0[2]};
+
+	if (gpus > 1)
+	{
+		if (test || test2 || b_accuracy) return fail("Error: -test, -test2 and -accuracy run on one GPU (drop -gpus).");
+		return run_multi_gpu(gpus, cfg, scheme, host, nBodies, par, dt, nIters, nSteps, strout);
+	}
 
 	Device d;
 	const int64_t n = nBodies;

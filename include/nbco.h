@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NBCO_ABI_VERSION 2
+#define NBCO_ABI_VERSION 3
 
 typedef struct nbco_ctx nbco_ctx;
 
@@ -64,6 +64,11 @@ typedef struct nbco_config
 	int32_t world;         /* compute only this rank's shard of targets (see nbco_shard_range)      */
 	double  eps2_d;        /* EPS2 of the 2D fp64 path (SCAL = double, constants.cuh:39); default 1e-18;
 	                          0 = use (double)eps2 */
+	int32_t reproducible;  /* 3D kd FMM, orders 1..6.  0 (default): pair lists, float atomics like the reference (forces
+	                          differ from run to run in the last bits).  1: lists bucketed by target and sorted, every
+	                          local expansion and acceleration is one sum in registers: bit-reproducible forces, no
+	                          atomics, about 1.6x the evaluation time */
+	int32_t reserved0;
 } nbco_config;
 
 #define NBCO_MAX_ORDER 10   /* 3D kd-tree FMM: 1..6 unrolled templates, 7..10 runtime-order loops (main3.cu:790-811 sweeps 1..10) */
@@ -238,6 +243,14 @@ int nbco_beam_params2(const double *omega0_2, const double *emit2, double tune_d
 int nbco_state_read2(const char *path, double **h_pos_vel, int64_t *n);  /* caller frees with nbco_free */
 int nbco_state_write2(const char *path, const double *h_pos_vel, int64_t n);
 
+/* ---- particle identity (optional) ----
+ * With unsort = 0 the evaluator permutes pos / vel into tree order at every rebuild and the reference loses the
+ * particles' identity there (d_unsort is reset to iota, fmm_cart3_kdtree.cuh:1626).  nbco_track_ids registers a
+ * device array of n int32 that is permuted together with pos / vel from then on (ids[j] = id of the particle now
+ * stored at j); pass NULL to stop.  The caller initialises it (e.g. 0 .. n-1) and owns the memory.  Not available
+ * while peers are attached. */
+int nbco_track_ids(nbco_ctx *ctx, int32_t *d_ids);
+
 /* ---- multi-GPU helpers ---- */
 /* Target shard [begin, end) of rank r of w over n items: the kd-tree's own equal split
  * ceil(n*r/w) (fmm_cart3_kdtree.cuh:117-118). */
@@ -251,8 +264,8 @@ void nbco_shard_range(int64_t n, int32_t rank, int32_t world, int64_t *begin, in
  *   nbco_peer_export(ctx, n, handles)            192 bytes = 3 cudaIpcMemHandle_t, to be sent to every other rank
  *   nbco_peer_attach(ctx, q, handles_of_q)       for every q != rank
  *   nbco_peer_commit(ctx)
- * From then on nbco_force_fmm3_kd / nbco_coulomb_fmm3_kd / nbco_compute_force / nbco_integrate (leapfrog) must be
- * called by all ranks together with the same n.  The FIRST evaluation expects the full, identical [pos | vel] on
+ * From then on nbco_force_fmm3_kd / nbco_coulomb_fmm3_kd / nbco_compute_force / nbco_integrate must be
+ * called by all ranks together with the same n (all four schemes).  The FIRST evaluation expects the full, identical [pos | vel] on
  * every rank; afterwards every rank holds (and steps) only its own range, and tree rebuilds fetch the other
  * ranges from their owners.  nbco_peer_gather leaves the full [pos | vel | acc] on every rank again. */
 int nbco_peer_export(nbco_ctx *ctx, int64_t n, void *h_handles192);

@@ -69,6 +69,18 @@ def test_fmm_options_match_oracle(cfg):
     check_against_oracle(st[0], st[1], nb.default_param(n), 3, 1, **cfg)
 
 
+@pytest.mark.parametrize("n,order,m2l_first", [(20011, 1, 1), (100003, 3, 1), (65536, 5, 0), (1 << 18, 3, 1)])
+def test_fmm_reproducible_mode_matches_oracle_and_repeats_bit_for_bit(n, order, m2l_first):
+    """cfg.reproducible = 1: interaction lists bucketed by target and sorted, every local expansion and acceleration
+    is one sum in registers (no float atomics): same tree / lists / tolerance as the default flow, and two
+    evaluations of the same input give IDENTICAL bits (the default flow differs in the last bits from run to run)"""
+    st = nb.init_ga(n)
+    par = nb.default_param(n)
+    ctx, acc, T = check_against_oracle(st[0], st[1], par, order, m2l_first, reproducible=1)
+    acc2 = nb.Context(order=order, unsort=0, m2l_first=m2l_first, reproducible=1).eval_host(nb.EVAL_FMM3_KD, st[0].copy(), st[1].copy(), par)
+    assert np.array_equal(acc, acc2)
+
+
 def test_fmm_config2_size_matches_oracle_and_direct():
     """BASELINE config 2: N = 2^20, p = 3, fp32 -- tree/lists bit-exact, forces <= 1e-5, and the FMM
     error against the direct sum no worse than the reference algorithm's (oracle)"""
@@ -207,6 +219,32 @@ def test_fmm_unsort_mode_and_fused_elastic():
     a2 = c1.eval_host(nb.EVAL_COULOMB_FMM3_KD, st[0].copy(), st[1].copy(), par)
     want = a1 - st[0] * par[3:6]
     assert np.abs(a2 - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_track_ids_follow_the_particles_through_rebuilds():
+    """optional identity array (the reference loses identity at every rebuild, fmm_cart3_kdtree.cuh:1626): after several
+    rebuilds ids[j] still names the input particle stored at j -- a run with unsort = 1 (input order kept) is the check"""
+    import torch
+    n, steps = 40000, 9
+    st = nb.init_ga(n)
+    par = torch.from_numpy(nb.default_param(n)).cuda()
+    ev = nb.EVAL_COULOMB_FMM3_KD
+    bufs = []
+    for unsort in (0, 1):
+        c = nb.Context(order=3, unsort=unsort, tree_steps=4)
+        b = torch.zeros(9 * n, dtype=torch.float32, device="cuda")
+        b[:6 * n] = torch.from_numpy(st.ravel()).cuda()
+        ids = torch.arange(n, dtype=torch.int32, device="cuda")
+        if not unsort:
+            c.track_ids(ids.data_ptr())
+        c.compute_force(ev, b.data_ptr(), n, par.data_ptr())
+        c.integrate(nb.LEAPFROG, ev, b.data_ptr(), n, par.data_ptr(), 5e-4, steps)
+        bufs.append((b.cpu().numpy().reshape(3, n, 3), ids.cpu().numpy()))
+    (s0, ids0), (s1, _) = bufs
+    assert np.array_equal(np.sort(ids0), np.arange(n)) and not np.array_equal(ids0, np.arange(n))
+    # tree_steps = 4 with unsort = 1 rebuilds at every evaluation: the trajectories agree only to the FMM's accuracy class
+    assert np.abs(s0[0] - s1[0][ids0]).max() <= 1e-4 * np.abs(s1[0]).max()
+    assert np.abs(s0[1] - s1[1][ids0]).max() <= 2e-2 * np.abs(s1[1]).max()
 
 
 def test_fmm_tree_reuse_between_rebuilds():

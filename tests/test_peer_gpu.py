@@ -146,6 +146,50 @@ def test_peer_gather_then_continue_across_a_rebuild():
         c.peer_detach()
 
 
+@pytest.mark.parametrize("scheme", [nb.EULER, nb.FORESTRUTH, nb.PEFRL])
+def test_peer_ranks_run_every_integrator(scheme):
+    """peer mode steps the rank's own range under all four schemes of integrator.cuh:32-167 (round 1: leapfrog only);
+    Forest-Ruth / PEFRL evaluate the force 3 / 4 times per step, so 3 steps cross a tree rebuild (tree_steps = 4)"""
+    import torch
+    world, n, steps = 2, 50000, 3
+    st = nb.init_ga(n)
+    par = torch.from_numpy(nb.default_param(n)).cuda()
+
+    def state():
+        b = torch.zeros(9 * n, dtype=torch.float32, device="cuda")
+        b[:6 * n] = torch.from_numpy(st.ravel()).cuda()
+        return b
+
+    c1 = nb.Context(order=3, unsort=0, tree_steps=4)
+    b1 = state()
+    c1.compute_force(EV, b1.data_ptr(), n, par.data_ptr())
+    c1.integrate(scheme, EV, b1.data_ptr(), n, par.data_ptr(), 5e-4, steps)
+    want = b1.cpu().numpy().reshape(3, n, 3)
+    ctxs = [nb.Context(order=3, unsort=0, tree_steps=4, rank=r, world=world) for r in range(world)]
+    bufs = [state() for _ in range(world)]
+    torch.cuda.synchronize()
+    for c in ctxs:
+        c.peer_export(n)
+    for r, c in enumerate(ctxs):
+        c.peer_attach_local(1 - r, ctxs[1 - r])
+        c.peer_commit()
+
+    def rank_main(r):
+        torch.cuda.set_device(0)
+        c, b = ctxs[r], bufs[r]
+        c.compute_force(EV, b.data_ptr(), n, par.data_ptr())
+        c.integrate(scheme, EV, b.data_ptr(), n, par.data_ptr(), 5e-4, steps)
+        c.peer_gather(b.data_ptr(), n)
+
+    run_ranks(rank_main, world)
+    for r in range(world):
+        got = bufs[r].cpu().numpy().reshape(3, n, 3)
+        assert np.abs(got[0] - want[0]).max() <= 1e-6 * np.abs(want[0]).max(), r
+        assert np.abs(got[1] - want[1]).max() <= 1e-5 * np.abs(want[1]).max(), r
+    for c in ctxs:
+        c.peer_detach()
+
+
 def test_peer_mode_errors():
     c = nb.Context(order=3, unsort=1, rank=0, world=2)
     with pytest.raises(nb.NbcoError, match="unsort"):
