@@ -43,6 +43,21 @@ __global__ void __launch_bounds__(256) gather3_kernel(const float *__restrict__ 
 	}
 }
 
+// peer mode: zero the locals of rank r's own subtree only (levels g .. L; the replicated top is cleared by a small
+// memset).  A full-size memset costs 64 B x all nodes on every rank and does not shrink with the number of GPUs.
+__global__ void __launch_bounds__(256) zero_own_locals_kernel(float4 *__restrict__ local4, int q4 /* float4 per node */, int L, int r, int g)
+{
+	const int64_t own_nodes = ((int64_t)1 << (L - g + 1)) - 1; // heap order inside the own subtree
+	const int64_t total = own_nodes * q4, stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride)
+	{
+		const int64_t m = k / q4;
+		const int lo = 63 - __clzll(m + 1);
+		const int64_t node = kd_beg(g + lo) + ((int64_t)r << lo) + (m + 1 - ((int64_t)1 << lo));
+		local4[node * q4 + (k - m * q4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+}
+
 __global__ void __launch_bounds__(256) gather1_kernel(const int *__restrict__ src, const int *__restrict__ perm, int *__restrict__ dst, int64_t n)
 {
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1106,7 +1121,18 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	// (opt-in: cfg.reproducible.  Measured on B200 at N = 2^24: the gather per target is load-imbalanced -- rows hold 0..30
 	// sources -- and costs 2.3 ms per evaluation against 0.84 ms for the pair kernels: profiles/r02_notes.md)
 	const bool by_target = ops.by_target && c.reproducible;
-	if (!by_target) NBCO_CUDA(cudaMemsetAsync(p.local.p, 0, sizeof(float) * (size_t)p.ntot * p.sL, st));
+	if (!by_target)
+	{
+		if (peer && pg > 0)
+		{
+			NBCO_CUDA(cudaMemsetAsync(p.local.p, 0, sizeof(float) * (size_t)kd_beg(pg) * p.sL, st)); // replicated top levels
+			const int64_t work = ((((int64_t)1 << (L - pg + 1)) - 1) * (p.sL / 4));
+			zero_own_locals_kernel<<<grid_for(work, 256, ctx->sm_count, 8), 256, 0, st>>>(p.local.as<float4>(), p.sL / 4, L, pr, pg);
+			LAUNCHED(ctx);
+		}
+		else
+			NBCO_CUDA(cudaMemsetAsync(p.local.p, 0, sizeof(float) * (size_t)p.ntot * p.sL, st));
+	}
 	if (peer) NBCO_TRY(peer_publish(ctx, d_pos, 0, n));
 	ops.upward(ctx, t, spos, n, L, pr, pg, 0);
 	if (peer)

@@ -70,6 +70,38 @@ leaf_p2m_kernel(TreeData t, const float *__restrict__ spos, int64_t n, int L, in
 	}
 }
 
+// Uniform leaves (n a multiple of 2^L: every power-of-two N) of exactly 8 particles: a leaf is 96 contiguous, 16-byte
+// aligned bytes, moved as six float4 instead of 24 scalar loads (the scalar version is bound by L1 wavefronts: ncu,
+// profiles/r01_notes.md); the centre is still the sequential fp32 sum in storage order (bit-exact).
+template <int P>
+__global__ void __launch_bounds__(128)
+leaf_p2m_u8_kernel(TreeData t, const float *__restrict__ spos, int L, int first, int count)
+{
+	const int beg = kd_beg(L);
+	for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < first + count; i += gridDim.x * blockDim.x)
+	{
+		float c[24];
+		const float4 *src = reinterpret_cast<const float4 *>(spos + 24 * (int64_t)i);
+#pragma unroll
+		for (int k = 0; k < 6; ++k) { const float4 v = src[k]; c[4*k] = v.x; c[4*k+1] = v.y; c[4*k+2] = v.z; c[4*k+3] = v.w; }
+		float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) { cx += c[3*j]; cy += c[3*j+1]; cz += c[3*j+2]; }
+		cx = __fdiv_rn(cx, 8.f); cy = __fdiv_rn(cy, 8.f); cz = __fdiv_rn(cz, 8.f);
+		t.center[beg + i] = make_float4(cx, cy, cz, t.size2[beg + i]);
+		float M[pad4<sym_off(P)>()];
+#pragma unroll
+		for (int k = 0; k < pad4<sym_off(P)>(); ++k) M[k] = 0.f;
+		if constexpr (P >= 3)
+		{
+#pragma unroll
+			for (int j = 0; j < 8; ++j) p2m_acc<P>(M, c[3*j] - cx, c[3*j+1] - cy, c[3*j+2] - cz);
+		}
+		M[0] = 8.f;
+		store_tuple<sym_off(P)>(t.mpole + (int64_t)(beg + i) * t.sM, M);
+	}
+}
+
 // same result with G lanes per leaf, for leaves of more than 8 particles (orders >= 4): particles are
 // loaded one per lane, the centre is still the SEQUENTIAL fp32 sum (lane 0 adds the shuffled values in
 // storage order, bit-exact), the P2M sums are accumulated per lane and reduced by butterfly shuffles
@@ -524,6 +556,64 @@ l2p_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__
 }
 
 
+// L2P for uniform leaves of C particles (n a multiple of 2^L, C = n / 2^L in {8, 16, 32}): leaf = j / C without the
+// ceil-division bookkeeping, the leaf's particles read as float4 (3 C / 4 of them, shared by the lanes of the leaf through
+// L1), the intra-leaf near field fully unrolled
+template <int P, int C>
+__global__ void __launch_bounds__(128)
+l2p_uniform_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__ acc_near, float *__restrict__ acc_out,
+                   const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int L, int64_t j_lo, int64_t j_hi, float eps2, int coll)
+{
+	const float scale = param ? param[0] : 1.f;
+	float k3[3] = {1.f, 1.f, 1.f};
+	if (fuse_elastic && param) { k3[0] = param[3]; k3[1] = param[4]; k3[2] = param[5]; }
+	const int beg = kd_beg(L);
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t j = j_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < j_hi; j += stride)
+	{
+		const int leaf = (int)(j / C), me = (int)(j % C);
+		const float4 c = t.center[beg + leaf];
+		float Lq[pad4<trl_off(P + 1)>()], S[sym_off(P + 1)];
+		load_tuple<trl_off(P + 1)>(Lq, t.local + (int64_t)(beg + leaf) * t.sL);
+		S[0] = 0.f;
+		local_expand<P>(S, Lq);
+		const float4 *src = reinterpret_cast<const float4 *>(spos + 3 * (int64_t)leaf * C);
+		const float x = spos[3*j], y = spos[3*j+1], z = spos[3*j+2];
+		float f[3];
+		l2p_field<P>(f, S, x - c.x, y - c.y, z - c.z);
+		if (coll)
+		{
+			float ax = 0.f, ay = 0.f, az = 0.f;
+			// four particles per three float4
+#pragma unroll
+			for (int q = 0; q < C / 4; ++q)
+			{
+				const float4 v0 = src[3*q], v1 = src[3*q+1], v2 = src[3*q+2];
+				const float sx[4] = {v0.x, v0.w, v1.z, v2.y}, sy[4] = {v0.y, v1.x, v1.w, v2.z}, sz[4] = {v0.z, v1.y, v2.x, v2.w};
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+				{
+					const float dx = x - sx[k], dy = y - sy[k], dz = z - sz[k];
+					float r2 = fmaf(dx, dx, eps2);
+					r2 = fmaf(dy, dy, r2);
+					r2 = fmaf(dz, dz, r2);
+					float w;
+					asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(r2));
+					w = w * fmaf(-0.5f * r2 * w, w, 1.5f);
+					const float w3 = (w * w) * w;
+					ax = fmaf(dx, w3, ax); ay = fmaf(dy, w3, ay); az = fmaf(dz, w3, az);
+				}
+			}
+			(void)me;
+			f[0] += ax; f[1] += ay; f[2] += az;
+		}
+		float ax = (acc_near[3*j] + f[0]) * scale, ay = (acc_near[3*j+1] + f[1]) * scale, az = (acc_near[3*j+2] + f[2]) * scale;
+		if (fuse_elastic) { ax = fmaf(-k3[0], x, ax); ay = fmaf(-k3[1], y, ay); az = fmaf(-k3[2], z, az); }
+		const int64_t o = perm_or_null ? (int64_t)perm_or_null[j] : j;
+		acc_out[3*o] = ax; acc_out[3*o+1] = ay; acc_out[3*o+2] = az;
+	}
+}
+
 constexpr int kTopLevels = 7; // levels 0..7 of the upward / 2..8 of the downward pass run in one CTA
 constexpr int kWideLevel = 1 << 16; // nodes of one rank at a level from which the level gets its own launch
 constexpr int kSubLevels = 7; // deeper levels: chunks of 7 levels, one CTA per subtree (128 nodes at its widest level)
@@ -541,7 +631,9 @@ struct OrderImpl
 		}
 		const int mlt_max = (int)((n - 1) / (1ll << L) + 1);
 		const int first = r << (L - g), count = 1 << (L - g);
-		if (mlt_max <= 8) leaf_p2m_kernel<P><<<grid_for(count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
+		const bool uniform = (n & ((1ll << L) - 1)) == 0; // every leaf holds exactly n / 2^L particles
+		if (uniform && mlt_max == 8) leaf_p2m_u8_kernel<P><<<grid_for(count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, L, first, count);
+		else if (mlt_max <= 8) leaf_p2m_kernel<P><<<grid_for(count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
 		else if (mlt_max <= 16) leaf_p2m_group_kernel<P, 16><<<grid_for(16ll * count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
 		else leaf_p2m_group_kernel<P, 32><<<grid_for(32ll * count, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, n, L, first, count);
 		++ctx->launches;
@@ -635,8 +727,16 @@ struct OrderImpl
 		}
 		if (ev_l2p) cudaEventRecord(ev_l2p, st);
 		const int64_t j_lo = seg_start(n, r, g), j_hi = seg_start(n, r + 1, g);
-		l2p_kernel<P><<<grid_for(j_hi - j_lo, 128, ctx->sm_count, 16), 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null,
-		                                                                              param, fuse_elastic, n, L, j_lo, j_hi, eps2, coll);
+		const bool uniform = (n & ((1ll << L) - 1)) == 0;
+		const int64_t C = n >> L;
+		const int grid = grid_for(j_hi - j_lo, 128, ctx->sm_count, 16);
+#define NBCO_L2P_UNIFORM(CC) l2p_uniform_kernel<P, CC><<<grid, 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null, param, fuse_elastic, L, j_lo, j_hi, eps2, coll)
+		if (uniform && C == 8) NBCO_L2P_UNIFORM(8);
+		else if (uniform && C == 16) NBCO_L2P_UNIFORM(16);
+		else if (uniform && C == 32) NBCO_L2P_UNIFORM(32);
+		else
+			l2p_kernel<P><<<grid, 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null, param, fuse_elastic, n, L, j_lo, j_hi, eps2, coll);
+#undef NBCO_L2P_UNIFORM
 		++ctx->launches;
 	}
 };

@@ -325,13 +325,22 @@ top_resolve_kernel(float4 *__restrict__ out, float4 *__restrict__ scratch, TreeG
 			const u32 mask = pass == 2 ? 1023u : 2047u;
 			for (int b = tid; b < kBins; b += kResThreads) sh[b] = 0;
 			__syncthreads();
-			for (u32 i = tid; i < eq; i += kResThreads)
+			// four independent loads per thread and trip: one CTA walks up to ~64 k candidates (root level), latency-bound
+			for (u32 i0 = tid; i0 < eq; i0 += 4 * kResThreads)
 			{
-				const Words W = words_of(C[i], chain);
-				bool m = true;
-				for (int e = 0; e < d; ++e) m = m && W.w[e] == piv[e];
-				if (pass > 0) m = m && (W.w[d] >> (shift + (pass == 1 ? 11 : 10))) == (prefix >> (shift + (pass == 1 ? 11 : 10)));
-				if (m) atomicAdd(&sh[(W.w[d] >> shift) & mask], 1u);
+				float4 q[4];
+#pragma unroll
+				for (int k = 0; k < 4; ++k) { const u32 i = i0 + k * kResThreads; q[k] = i < eq ? C[i] : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+				{
+					if (i0 + k * kResThreads >= eq) continue;
+					const Words W = words_of(q[k], chain);
+					bool m = true;
+					for (int e = 0; e < d; ++e) m = m && W.w[e] == piv[e];
+					if (pass > 0) m = m && (W.w[d] >> (shift + (pass == 1 ? 11 : 10))) == (prefix >> (shift + (pass == 1 ? 11 : 10)));
+					if (m) atomicAdd(&sh[(W.w[d] >> shift) & mask], 1u);
+				}
 			}
 			__syncthreads();
 			find_rank_bin(sh, r, wsum, found);
@@ -346,44 +355,69 @@ top_resolve_kernel(float4 *__restrict__ out, float4 *__restrict__ scratch, TreeG
 	}
 
 	// ---- split the candidates: lexicographic (w[0 .. depth)) <= piv goes left ----
+	// four rows of kResThreads candidates per trip (independent loads, one pair of barriers per 4096 candidates)
+	__shared__ u32 rowcnt[4][32];
 	if (tid == 0) { run[0] = 0; run[1] = 0; s_minr = 0xffffffffu; }
 	__syncthreads();
 	u32 minr = 0xffffffffu;
-	for (u32 base = 0; base < eq; base += kResThreads)
+	for (u32 base = 0; base < eq; base += 4 * kResThreads)
 	{
-		const u32 i = base + tid;
-		const bool valid = i < eq;
-		float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-		bool left = false;
-		if (valid)
+		float4 q[4];
+		bool valid[4], left[4];
+		u32 bl[4], br[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
 		{
-			p = C[i];
-			const Words W = words_of(p, chain);
-			left = true; // equal on every compared word: the pivot itself or a tie that goes left
-			for (int e = 0; e < depth; ++e)
-				if (W.w[e] != piv[e]) { left = W.w[e] < piv[e]; break; }
-			if (!left) minr = min(minr, W.w[0]);
+			const u32 i = base + k * kResThreads + tid;
+			valid[k] = i < eq;
+			q[k] = valid[k] ? C[i] : make_float4(0.f, 0.f, 0.f, 0.f);
 		}
-		const u32 bl = __ballot_sync(0xffffffffu, valid && left), br = __ballot_sync(0xffffffffu, valid && !left);
-		if (lane == 0) { wsum[w] = (u32)__popc(bl) | ((u32)__popc(br) << 16); }
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			left[k] = false;
+			if (valid[k])
+			{
+				const Words W = words_of(q[k], chain);
+				left[k] = true; // equal on every compared word: the pivot itself or a tie that goes left
+				for (int e = 0; e < depth; ++e)
+					if (W.w[e] != piv[e]) { left[k] = W.w[e] < piv[e]; break; }
+				if (!left[k]) minr = min(minr, W.w[0]);
+			}
+			bl[k] = __ballot_sync(0xffffffffu, valid[k] && left[k]);
+			br[k] = __ballot_sync(0xffffffffu, valid[k] && !left[k]);
+			if (lane == 0) rowcnt[k][w] = (u32)__popc(bl[k]) | ((u32)__popc(br[k]) << 16);
+		}
 		__syncthreads();
 		u32 ol = run[0], orr = run[1];
-		for (int k = 0; k < w; ++k) { ol += wsum[k] & 0xffffu; orr += wsum[k] >> 16; }
-		if (valid) T[left ? ol + __popc(bl & ((1u << lane) - 1u)) : need + orr + __popc(br & ((1u << lane) - 1u))] = p;
-		__syncthreads();
-		if (tid == 0)
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
 		{
-			u32 tl = 0, tr = 0;
-			for (int k = 0; k < 32; ++k) { tl += wsum[k] & 0xffffu; tr += wsum[k] >> 16; }
-			run[0] += tl; run[1] += tr;
+			u32 pl = ol, pr = orr;
+			for (int ww = 0; ww < 32; ++ww)
+			{
+				const u32 c = rowcnt[k][ww];
+				if (ww < w) { pl += c & 0xffffu; pr += c >> 16; }
+				ol += c & 0xffffu; orr += c >> 16;
+			}
+			if (valid[k]) T[left[k] ? pl + __popc(bl[k] & ((1u << lane) - 1u)) : need + pr + __popc(br[k] & ((1u << lane) - 1u))] = q[k];
 		}
+		__syncthreads();
+		if (tid == 0) { run[0] = ol; run[1] = orr; }
 		__syncthreads();
 	}
 	minr = __reduce_min_sync(0xffffffffu, minr);
 	if (lane == 0 && minr != 0xffffffffu) atomicMin(&s_minr, minr);
 	__threadfence_block();
 	__syncthreads();
-	for (u32 i = tid; i < eq; i += kResThreads) C[i] = T[i];
+	for (u32 i0 = tid; i0 < eq; i0 += 4 * kResThreads)
+	{
+		float4 q[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) { const u32 i = i0 + k * kResThreads; if (i < eq) q[k] = T[i]; }
+#pragma unroll
+		for (int k = 0; k < 4; ++k) { const u32 i = i0 + k * kResThreads; if (i < eq) C[i] = q[k]; }
+	}
 
 	// ---- boxes of the children: cut at the last particle of the left and the first of the right child ----
 	if (tid == 0)

@@ -136,3 +136,75 @@ def fmm_leapfrog_peer(ctx, buf, n, d_param, dt, nsteps, gather_final=True):
     ctx.integrate(LEAPFROG, EVAL_COULOMB_FMM3_KD, buf.data_ptr(), n, d_param, dt, nsteps)
     if gather_final:
         ctx.peer_gather(buf.data_ptr(), n)
+
+
+# ---- 2D fp64 FMM over several GPUs (SURVEY.md section 8e, row 3) ----
+def _ld(x):
+    return np.longdouble(x)
+
+
+def scheme_schedule(scheme, dt):
+    """[(op, coefficient)] of one step of integrator.cuh:32-167: op 'K' (v += c a), 'D' (x += c v), 'F' (a = f(x)).
+    Coefficients are formed in long double and cast to the scalar type at the call, like the reference."""
+    from ._lib import EULER, LEAPFROG, FORESTRUTH, PEFRL
+    dt = _ld(dt)
+    if scheme == EULER:
+        return [("K", dt), ("D", dt), ("F", None)]
+    if scheme == LEAPFROG:
+        return [("K", dt * _ld(0.5)), ("D", dt), ("F", None), ("K", dt * _ld(0.5))]
+    if scheme == FORESTRUTH:
+        th = _ld("1.3512071919596576340476878089715")
+        return [("D", dt * th / 2), ("F", None), ("K", dt * th), ("D", dt * (1 - th) / 2), ("F", None), ("K", dt * (1 - 2 * th)),
+                ("D", dt * (1 - th) / 2), ("F", None), ("K", dt * th), ("D", dt * th / 2)]
+    if scheme == PEFRL:
+        xi, la, ch = _ld("0.1786178958448091E+00"), _ld("-0.2123418310626054E+00"), _ld("-0.6626458266981849E-01")
+        return [("D", dt * xi), ("F", None), ("K", dt * (1 - 2 * la) / 2), ("D", dt * ch), ("F", None), ("K", dt * la),
+                ("D", dt * (1 - 2 * (ch + xi))), ("F", None), ("K", dt * la), ("D", dt * ch), ("F", None),
+                ("K", dt * (1 - 2 * la) / 2), ("D", dt * xi)]
+    raise ValueError(scheme)
+
+
+def fmm2_integrate_sharded(ctx, scheme, buf, n, d_param, dt, nsteps, group=None):
+    """nsteps steps of a symplectic scheme over coulombOscillatorFMM (2D fp64, main.cu) on `world` GPUs, one process
+    per GPU.  Every rank holds the full state and integrates it (kick / drift are 48 B per particle); the force evaluation
+    -- nbco_coulomb_fmm2 with cfg.rank / cfg.world -- sorts and summarises all particles on every rank (the tree is
+    replicated) and runs the dominant near-field + L2P kernel on the rank's own range of the cell-sorted particles; the
+    ranges of the accelerations are exchanged with ONE NCCL all-gather per evaluation (the real exchange step of this
+    path).  buf: torch float64 [pos | vel | acc] (6 n), identical on all ranks at entry."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    assert ctx.cfg.rank == rank and ctx.cfg.world == world
+    p0 = buf.data_ptr()
+    pos, vel, acc = p0, p0 + 8 * 2 * n, p0 + 8 * 4 * n
+    sizes = shard_sizes(n, world)
+    b, e = shard_range(n, rank, world)
+    acc_t = buf[4 * n:]
+    equal = len(set(sizes)) == 1
+
+    def force():
+        ctx.coulomb_fmm2(pos, acc, n, d_param)          # writes acc[b:e] (cell order; pos / vel permuted identically on all ranks)
+        if world == 1:
+            return
+        if equal:
+            dist.all_gather_into_tensor(acc_t, acc_t[2 * b:2 * e].clone(), group=group)
+        else:
+            pad = 2 * max(sizes)
+            tmp = torch.zeros(pad, dtype=acc_t.dtype, device=acc_t.device)
+            tmp[:2 * (e - b)] = acc_t[2 * b:2 * e]
+            out = [torch.empty_like(tmp) for _ in range(world)]
+            dist.all_gather(out, tmp, group=group)
+            acc_t.copy_(torch.cat([o[:2 * s] for o, s in zip(out, sizes)]))
+        if acc_t.is_cuda:
+            torch.cuda.current_stream().synchronize()
+
+    sched = scheme_schedule(scheme, dt)
+    for _ in range(nsteps):
+        for op, c in sched:
+            if op == "K":
+                ctx.step2(vel, acc, float(c), n)
+            elif op == "D":
+                ctx.step2(pos, vel, float(c), n)
+            else:
+                force()

