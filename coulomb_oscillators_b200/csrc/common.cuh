@@ -45,7 +45,13 @@ struct FmmPlan; // fmm3.cu
 
 // Multi-GPU over peer memory (peer.cu): what this rank publishes and what it has mapped from the others.
 constexpr int kPeerMax = 8;
-constexpr size_t kPeerHeader = 1024; // bytes of flag words at the start of the published buffer
+// published buffer of a rank: [flag words (kPeerHeader) | scratch of the distributed kd build (kPeerScratch) |
+//   tree-ordered positions 12 n | velocities 12 n | (16-byte aligned) record buffers A and B, 16 n each]
+constexpr size_t kPeerHeader = 1024;
+constexpr size_t kPeerScratch = 256 * 1024;
+constexpr size_t kPeerData = kPeerHeader + kPeerScratch;
+inline size_t peer_pay_offset(int64_t n, int which) { return ((kPeerData + 24 * (size_t)n + 15) & ~(size_t)15) + (size_t)which * 16 * (size_t)n; }
+inline size_t peer_pub_bytes(int64_t n) { return peer_pay_offset(n, 2); }
 struct PeerState
 {
 	bool active = false;

@@ -66,14 +66,15 @@ __global__ void __launch_bounds__(256) gather1_kernel(const int *__restrict__ sr
 
 // peer mode: the velocity of sorted particle j comes from whoever held its pre-rebuild index (tree-order ranges
 // are fixed index ranges, so that is rank floor(2^g idx / n)); most particles stay on their rank between rebuilds
-struct VelSrc { const float *v[kMaxPeers]; int g, me; };
+struct VelSrc { const float *v[kMaxPeers]; int g, me; u32 *dbg; };
 __global__ void __launch_bounds__(256) gather3_peer_kernel(VelSrc src, const int *__restrict__ perm, float *__restrict__ dst, int64_t cnt, int64_t n)
 {
 	const unsigned long long magic = ~0ull / (unsigned long long)n;
 	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
 	for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += stride)
 	{
-		const int64_t s = perm[j];
+		int64_t s = perm[j];
+		if (s < 0 || s >= n) { if (src.dbg) { src.dbg[40] = 300u; src.dbg[41] = (u32)j; src.dbg[42] = (u32)s; } s = 0; }
 		const float *v = src.v[owner_of(s, n, src.g, magic)];
 		dst[3*j] = v[3*s]; dst[3*j+1] = v[3*s+1]; dst[3*j+2] = v[3*s+2];
 	}
@@ -1059,7 +1060,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 		for (int q = 0; q < c.world; ++q)
 		{
 			t.peers.center[q] = (const float4 *)ps.center[q]; t.peers.mpole[q] = (const float *)ps.mpole[q];
-			t.peers.pos[q] = (const float *)((const char *)ps.pubp[q] + kPeerHeader);
+			t.peers.pos[q] = (const float *)((const char *)ps.pubp[q] + kPeerData);
 		}
 	const int64_t own_lo = seg_start(n, pr, pg), own_hi = seg_start(n, pr + 1, pg);
 
@@ -1073,19 +1074,31 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	}
 	else
 	{
-		if (peer && !ps.have_full)
+		// small trees: fewer shared-memory kd blocks than ranks -> every rank builds everything (needs all positions)
+		const int bg = pg <= p.kd.lt ? pg : 0;
+		const bool distributed = peer && bg > 0 && !getenv("NBCO_PEER_PULL_ALL");
+		if (distributed)
 		{
-			// every rank holds only its own range: publish it, pull the others' (the rebuild splits ALL particles)
-			// (positions only: the velocities of the particles that end up here are fetched after the build)
-			NBCO_TRY(peer_publish(ctx, d_pos, 0, n)); NBCO_TRY(peer_publish(ctx, d_pos + 3*n, 1, n));
-			NBCO_TRY(peer_barrier(ctx));
-			NBCO_TRY(peer_pull(ctx, d_pos, 0, n));
-			NBCO_TRY(peer_barrier(ctx)); // the position mirrors are rewritten below
+			// Distributed build (kdtree.cu): every rank contributes the records of its own range; the first g levels are
+			// selected from summed histograms, then every rank pulls the records of its subtree.  The velocities of the
+			// particles that end up here are fetched afterwards from the published velocity ranges.
+			NBCO_TRY(peer_publish(ctx, d_pos + 3*n, 1, n));
+			NBCO_TRY(kd_build_peer(ctx, p.kd, d_pos, p.ev[PH_KDBOTTOM], pr, pg, ps.pubp));
 			pulled = true;
 		}
-		// small trees: fewer shared-memory kd blocks than ranks -> every rank builds everything (all positions are here)
-		const int bg = pg <= p.kd.lt ? pg : 0;
-		NBCO_TRY(kd_build(ctx, p.kd, d_pos, p.ev[PH_KDBOTTOM], bg ? pr : 0, bg));
+		else
+		{
+			if (peer && !ps.have_full)
+			{
+				// every rank holds only its own range: publish it, pull the others' (this path splits ALL particles on every rank)
+				NBCO_TRY(peer_publish(ctx, d_pos, 0, n)); NBCO_TRY(peer_publish(ctx, d_pos + 3*n, 1, n));
+				NBCO_TRY(peer_barrier(ctx));
+				NBCO_TRY(peer_pull(ctx, d_pos, 0, n));
+				NBCO_TRY(peer_barrier(ctx)); // the position mirrors are rewritten below
+				pulled = true;
+			}
+			NBCO_TRY(kd_build(ctx, p.kd, d_pos, p.ev[PH_KDBOTTOM], bg ? pr : 0, bg));
+		}
 		NBCO_CUDA(cudaEventRecord(p.ev[PH_PERMUTE], st));
 		if (c.unsort)
 			spos = p.kd.spos.as<float>();
@@ -1098,8 +1111,9 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 			{
 				VelSrc vs;
 				for (int q = 0; q < kMaxPeers; ++q)
-					vs.v[q] = q < c.world ? (const float *)((const char *)ps.pubp[q] + kPeerHeader) + 3 * (size_t)n : nullptr;
+					vs.v[q] = q < c.world ? (const float *)((const char *)ps.pubp[q] + kPeerData) + 3 * (size_t)n : nullptr;
 				vs.v[pr] = d_pos + 3*n; vs.g = pg; vs.me = pr;
+				vs.dbg = getenv("NBCO_DEBUG_KD") ? (u32 *)((char *)ps.pub.p + 768) : nullptr;
 				gather3_peer_kernel<<<grid_for(cnt, 256, ctx->sm_count, 8), 256, 0, st>>>(vs, p.kd.perm.as<int>() + own_lo, p.tmp3.as<float>() + 3*own_lo, cnt, n);
 			}
 			else
@@ -1394,6 +1408,15 @@ int fmm3_harvest(nbco_ctx *ctx, int *overflow)
 	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
 	unsigned perr = 0;
 	if (ctx->peer.active) NBCO_TRY(peer_report_error(ctx, &perr));
+	if (ctx->peer.active && getenv("NBCO_DEBUG_KD"))
+	{
+		u32 dw[48];
+		cudaMemcpy(dw, (char *)ctx->peer.pub.p + 768, sizeof(dw), cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[kd sanity rank %d] select %u %u %u %u %u %u %u | exchange %u %u %u : %u %u %u %u | split", ctx->cfg.rank, dw[0], dw[1], dw[2], dw[3],
+		        dw[4], dw[5], dw[6], dw[8], dw[9], dw[10], dw[11], dw[12], dw[13], dw[14]);
+		for (int k = 20; k < 32; ++k) fprintf(stderr, " %u", dw[k]);
+		fprintf(stderr, " | root %08x %08x %08x %08x %08x %08x | gather %u %u %u\n", dw[32], dw[33], dw[34], dw[35], dw[36], dw[37], dw[40], dw[41], dw[42]);
+	}
 	const int npend = p.ev_npend;
 	for (int k = 0; k < npend; ++k)
 	{

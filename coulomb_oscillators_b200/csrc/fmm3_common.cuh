@@ -135,6 +135,9 @@ int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L);
 // r, g: build the top g levels over all particles and, below them, only the subtree of node (g, r)
 // (g = 0: the whole tree)
 int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom, int r, int g);
+// distributed build over the ranks' published buffers (peer mode): no rank holds or partitions all particles
+int kd_build_peer(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom, int r, int g, void *const *pub);
+int kd_preload_kernels();   // force the (lazy) module loads of the build kernels
 void kd_release(KdTree &t);
 
 // leaf (or node of level l) that owns sorted position j: floor(2^l j / n) (:162-164) without a 64-bit

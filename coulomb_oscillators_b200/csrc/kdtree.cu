@@ -101,13 +101,16 @@ __global__ void root_box_kernel(TreeGeom g, const u32 *__restrict__ bb)
 // =====================================================================================
 struct TileRange { int64_t a, b, s0; int seg; };
 
-__device__ __forceinline__ TileRange tile_range(int64_t n, int l, int tps, int tile, int seg0)
+// lb != nullptr (distributed top levels, peer mode): segment s of this rank's records is [base + lb[s], base + lb[s+1])
+// (a table on the device: the local sizes are data dependent); else the global rule [seg_start(s), seg_start(s + 1))
+__device__ __forceinline__ TileRange tile_range(int64_t n, int l, int tps, int tile, int seg0, const int64_t *lb = nullptr, int64_t base = 0)
 {
 	TileRange r;
 	r.seg = seg0 + blockIdx.x / tps;
 	const int t = blockIdx.x % tps;
-	r.s0 = seg_start(n, r.seg, l);
-	const int64_t s1 = seg_start(n, r.seg + 1, l);
+	int64_t s1;
+	if (lb) { r.s0 = base + lb[r.seg]; s1 = base + lb[r.seg + 1]; }
+	else { r.s0 = seg_start(n, r.seg, l); s1 = seg_start(n, r.seg + 1, l); }
 	r.a = r.s0 + (int64_t)t * tile;
 	r.b = r.a + tile < s1 ? r.a + tile : s1;
 	return r;
@@ -115,12 +118,13 @@ __device__ __forceinline__ TileRange tile_range(int64_t n, int l, int tps, int t
 
 // histogram of the linear bins of every segment of level l
 __global__ void __launch_bounds__(kTopThreads)
-top_hist_kernel(const float4 *__restrict__ pay, TreeGeom g, u32 *__restrict__ hist, int64_t n, int l, int tps, int tile, int seg0)
+top_hist_kernel(const float4 *__restrict__ pay, TreeGeom g, u32 *__restrict__ hist, int64_t n, int l, int tps, int tile, int seg0,
+                const int64_t *__restrict__ lb = nullptr, int64_t base = 0)
 {
 	__shared__ u32 sh[kBins];
 	for (int b = threadIdx.x; b < kBins; b += kTopThreads) sh[b] = 0;
 	__syncthreads();
-	const TileRange r = tile_range(n, l, tps, tile, seg0);
+	const TileRange r = tile_range(n, l, tps, tile, seg0, lb, base);
 	const int node = kd_beg(l) + r.seg, axis = g.splitdim[node];
 	const float lo = g.lbound[3*node + axis], scale = bin_scale(lo, g.rbound[3*node + axis], kBins);
 	int64_t j = r.a + threadIdx.x;
@@ -188,12 +192,12 @@ top_pick_kernel(SegState *__restrict__ st, u32 *__restrict__ hist, int64_t n, in
 // three-way split of every segment by bin: [bins < pb | bin == pb (candidates) | bins > pb], unordered inside
 __global__ void __launch_bounds__(kTopThreads)
 top_partition_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, TreeGeom g, SegState *__restrict__ st,
-                     int64_t n, int l, int tps, int tile, int seg0)
+                     int64_t n, int l, int tps, int tile, int seg0, const int64_t *__restrict__ lb = nullptr, int64_t rbase = 0)
 {
 	constexpr int kWarps = kTopThreads / 32;
 	__shared__ u32 wcnt[kWarps][3];
 	__shared__ u32 base[3];
-	const TileRange r = tile_range(n, l, tps, tile, seg0);
+	const TileRange r = tile_range(n, l, tps, tile, seg0, lb, rbase);
 	if (r.a >= r.b) return;
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	const u32 lt_mask = (1u << lane) - 1u;
@@ -325,17 +329,317 @@ top_resolve_kernel(float4 *__restrict__ out, float4 *__restrict__ scratch, TreeG
 			const u32 mask = pass == 2 ? 1023u : 2047u;
 			for (int b = tid; b < kBins; b += kResThreads) sh[b] = 0;
 			__syncthreads();
-			// four independent loads per thread and trip: one CTA walks up to ~64 k candidates (root level), latency-bound
+			for (u32 i = tid; i < eq; i += kResThreads)
+			{
+				const Words W = words_of(C[i], chain);
+				bool m = true;
+				for (int e = 0; e < d; ++e) m = m && W.w[e] == piv[e];
+				if (pass > 0) m = m && (W.w[d] >> (shift + (pass == 1 ? 11 : 10))) == (prefix >> (shift + (pass == 1 ? 11 : 10)));
+				if (m) atomicAdd(&sh[(W.w[d] >> shift) & mask], 1u);
+			}
+			__syncthreads();
+			find_rank_bin(sh, r, wsum, found);
+			prefix |= found[0] << shift;
+			r -= found[1];
+			t = found[2];
+			__syncthreads();
+		}
+		piv[d] = prefix;
+		depth = d + 1;
+		if (t == 1u || r == t - 1u) break; // the pivot is unique, or every particle that ties with it goes left
+	}
+
+	// ---- split the candidates: lexicographic (w[0 .. depth)) <= piv goes left ----
+	if (tid == 0) { run[0] = 0; run[1] = 0; s_minr = 0xffffffffu; }
+	__syncthreads();
+	u32 minr = 0xffffffffu;
+	for (u32 base = 0; base < eq; base += kResThreads)
+	{
+		const u32 i = base + tid;
+		const bool valid = i < eq;
+		float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+		bool left = false;
+		if (valid)
+		{
+			p = C[i];
+			const Words W = words_of(p, chain);
+			left = true; // equal on every compared word: the pivot itself or a tie that goes left
+			for (int e = 0; e < depth; ++e)
+				if (W.w[e] != piv[e]) { left = W.w[e] < piv[e]; break; }
+			if (!left) minr = min(minr, W.w[0]);
+		}
+		const u32 bl = __ballot_sync(0xffffffffu, valid && left), br = __ballot_sync(0xffffffffu, valid && !left);
+		if (lane == 0) { wsum[w] = (u32)__popc(bl) | ((u32)__popc(br) << 16); }
+		__syncthreads();
+		u32 ol = run[0], orr = run[1];
+		for (int k = 0; k < w; ++k) { ol += wsum[k] & 0xffffu; orr += wsum[k] >> 16; }
+		if (valid) T[left ? ol + __popc(bl & ((1u << lane) - 1u)) : need + orr + __popc(br & ((1u << lane) - 1u))] = p;
+		__syncthreads();
+		if (tid == 0)
+		{
+			u32 tl = 0, tr = 0;
+			for (int k = 0; k < 32; ++k) { tl += wsum[k] & 0xffffu; tr += wsum[k] >> 16; }
+			run[0] += tl; run[1] += tr;
+		}
+		__syncthreads();
+	}
+	minr = __reduce_min_sync(0xffffffffu, minr);
+	if (lane == 0 && minr != 0xffffffffu) atomicMin(&s_minr, minr);
+	__threadfence_block();
+	__syncthreads();
+	for (u32 i = tid; i < eq; i += kResThreads) C[i] = T[i];
+
+	// ---- boxes of the children: cut at the last particle of the left and the first of the right child ----
+	if (tid == 0)
+	{
+		float lb[3], rb[3];
+		for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
+		const int pch = chain;
+		const float save = rb[axis];
+		rb[axis] = unordered_bits(piv[0]);
+		write_box(g, 2*node + 1, lb, rb, pch);
+		rb[axis] = save;
+		lb[axis] = unordered_bits(min(s_minr, s.rmin));
+		write_box(g, 2*node + 2, lb, rb, pch);
+	}
+}
+
+// =====================================================================================
+//  distributed top levels (peer mode): rank r holds N/G records; the first g = log2 G levels
+//  select their medians from per-rank histograms summed through the published scratch blocks, every rank splits its own
+//  records, the candidates of the pivot bin are ordered from the union of all ranks' candidates (read over NVLink), and
+//  after level g - 1 every rank pulls the records of its own subtree from wherever they are.  No rank ever holds, packs
+//  or partitions all N records (round 1 pulled all positions and built the top g levels over all particles everywhere).
+// =====================================================================================
+// scratch block of a rank (kPeerScratch bytes, published): byte offsets
+constexpr size_t kScrBBox = 0;                 // u32[6]: ordered bits of the local bounding box
+constexpr size_t kScrRange = 64;               // int64 lb[level 0 .. g][9]: local segment boundaries (relative to the rank's range)
+constexpr size_t kScrSeg = 1024;               // SegState[level][8]: LOCAL selection state (less = local count below the pivot bin,
+                                               // eq = local candidates, rmin = local minimum key right of the pivot bin)
+constexpr size_t kScrGlob = 2048;              // u32[level][8][2]: GLOBAL {less, eq} of the segment
+constexpr size_t kScrPivot = 2560;             // u32[level][8][8]: pivot words [0..3], depth, smallest right key (select -> split)
+constexpr size_t kScrHist = 4096;              // u32[level][segment][kBins]: local histograms, level l starts at (2^l - 1) rows
+static_assert(kScrHist + 7 * kBins * 4 <= kPeerScratch, "scratch block too small for 8 ranks");
+
+// sanity words of the distributed build (published header, byte 768; printed by fmm3_harvest when NBCO_DEBUG_KD is set)
+__device__ __forceinline__ u32 *kd_dbg(unsigned char *scr) { return reinterpret_cast<u32 *>(scr - 256); }
+
+struct PeerKd
+{
+	int world, me, g;
+	unsigned char *scr[kMaxPeers];   // scratch blocks
+	float4 *pay[kMaxPeers][2];       // record buffers
+	int64_t lo[kMaxPeers + 1];       // global range of rank q: [lo[q], lo[q+1])
+};
+__device__ __forceinline__ int64_t *scr_range(unsigned char *s, int l) { return reinterpret_cast<int64_t *>(s + kScrRange) + 9 * l; }
+__device__ __forceinline__ SegState *scr_seg(unsigned char *s, int l) { return reinterpret_cast<SegState *>(s + kScrSeg) + 8 * l; }
+__device__ __forceinline__ u32 *scr_glob(unsigned char *s, int l) { return reinterpret_cast<u32 *>(s + kScrGlob) + 16 * l; }
+__device__ __forceinline__ u32 *scr_pivot(unsigned char *s, int l) { return reinterpret_cast<u32 *>(s + kScrPivot) + 64 * l; }
+__device__ __forceinline__ u32 *scr_hist(unsigned char *s, int l) { return reinterpret_cast<u32 *>(s + kScrHist) + (size_t)((1 << l) - 1) * kBins; }
+
+__global__ void __launch_bounds__(256) pack_own_kernel(const float *__restrict__ pos, float4 *__restrict__ pay, int64_t lo, int64_t hi, u32 *__restrict__ out6)
+{
+	float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride)
+	{
+		const float x = pos[3*i], y = pos[3*i+1], z = pos[3*i+2];
+		pay[i] = make_float4(x, y, z, __uint_as_float((u32)i)); // id = global index in the previous tree order
+		mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
+		mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+		mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+	}
+#pragma unroll
+	for (int k = 0; k < 3; ++k)
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+			mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+		}
+	if ((threadIdx.x & 31) == 0)
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			atomicMin(out6 + k, ordered_bits(mn[k]));
+			atomicMax(out6 + 3 + k, ordered_bits(mx[k]));
+		}
+}
+
+__global__ void bbox_init_kernel(u32 *bb)
+{
+	if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
+	else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
+}
+
+// root box = union of the ranks' boxes (identical on every rank); local range table of level 0
+__global__ void root_box_peer_kernel(TreeGeom g, PeerKd pk)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0)
+	{
+		u32 mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+		for (int q = 0; q < pk.world; ++q)
+		{
+			const volatile u32 *bb = reinterpret_cast<const volatile u32 *>(pk.scr[q] + kScrBBox);
+			for (int k = 0; k < 3; ++k)
+			{
+				const u32 lo_k = bb[k], hi_k = bb[3 + k]; // plain unsigned compares (no overload resolution on volatile operands)
+				if (lo_k < mn[k]) mn[k] = lo_k;
+				if (hi_k > mx[k]) mx[k] = hi_k;
+			}
+		}
+		float lb[3], rb[3];
+		for (int k = 0; k < 3; ++k) { lb[k] = unordered_bits(mn[k]); rb[k] = unordered_bits(mx[k]); }
+		write_box(g, 0, lb, rb, kNoAxis | (kNoAxis << 2) | (kNoAxis << 4));
+		int64_t *r0 = scr_range(pk.scr[pk.me], 0);
+		r0[0] = 0; r0[1] = pk.lo[pk.me + 1] - pk.lo[pk.me];
+		u32 *dw = kd_dbg(pk.scr[pk.me]);
+		for (int k = 0; k < 3; ++k) { dw[32 + k] = mn[k]; dw[35 + k] = mx[k]; }
+	}
+}
+
+// one CTA per segment: sum the ranks' histograms, find the pivot bin (global rank), derive the LOCAL split counts
+__global__ void __launch_bounds__(256) top_pick_peer_kernel(PeerKd pk, int64_t n, int l)
+{
+	constexpr int kPer = kBins / 256;
+	__shared__ u32 wsum[8];
+	__shared__ u32 s_pb, s_less, s_eq, s_nl;
+	const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const u32 krank = (u32)(seg_start(n, 2 * (int64_t)seg + 1, l + 1) - seg_start(n, 2 * (int64_t)seg, l + 1)) - 1u;
+	u32 c[kPer], own[kPer], s = 0;
+#pragma unroll
+	for (int k = 0; k < kPer; ++k) c[k] = 0;
+	for (int q = 0; q < pk.world; ++q)
+	{
+		const volatile u32 *h = scr_hist(pk.scr[q], l) + (size_t)seg * kBins;
+#pragma unroll
+		for (int k = 0; k < kPer; ++k) { const u32 v = h[tid * kPer + k]; c[k] += v; if (q == pk.me) own[k] = v; }
+	}
+#pragma unroll
+	for (int k = 0; k < kPer; ++k) s += c[k];
+	u32 incl = s;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+	if (lane == 31) wsum[w] = incl;
+	__syncthreads();
+	u32 wbase = 0;
+	for (int i = 0; i < w; ++i) wbase += wsum[i];
+	const u32 excl = wbase + incl - s;
+	if (krank >= excl && krank < excl + s)
+	{
+		u32 run = excl;
+#pragma unroll
+		for (int k = 0; k < kPer; ++k)
+		{
+			if (krank >= run && krank < run + c[k]) { s_pb = (u32)(tid * kPer + k); s_less = run; s_eq = c[k]; }
+			run += c[k];
+		}
+	}
+	if (tid == 0) s_nl = 0;
+	__syncthreads();
+	// local records below the pivot bin
+	const u32 pb = s_pb;
+	u32 below = 0, at = 0;
+#pragma unroll
+	for (int k = 0; k < kPer; ++k)
+	{
+		const u32 bin = (u32)(tid * kPer + k);
+		if (bin < pb) below += own[k];
+		if (bin == pb) at = own[k];
+	}
+	below = __reduce_add_sync(0xffffffffu, below);
+	if (lane == 0 && below) atomicAdd(&s_nl, below);
+	__syncthreads();
+	if (tid * kPer <= (int)pb && (int)pb < (tid + 1) * kPer)
+	{
+		SegState z;
+		z.pb = pb; z.less = s_nl; z.eq = at; z.curL = z.curE = z.curR = 0; z.rmin = 0xffffffffu; z.pad = 0;
+		scr_seg(pk.scr[pk.me], l)[seg] = z;
+		u32 *gl = scr_glob(pk.scr[pk.me], l) + 2 * seg;
+		gl[0] = s_less; gl[1] = s_eq;
+	}
+}
+
+// union of the ranks' candidate lists of a segment, addressed by one index
+struct CandUnion
+{
+	const float4 *base[kMaxPeers];
+	u32 pre[kMaxPeers + 1];
+	int world;
+	__device__ __forceinline__ float4 at(u32 i) const
+	{
+		int q = 0;
+		while (q + 1 < world && i >= pre[q + 1]) ++q;
+		return base[q][i - pre[q]];
+	}
+};
+
+// One CTA per segment: the pivot of the UNION of all ranks' candidates (lexicographic radix select, identical on every
+// rank).  The result goes to this rank's scratch; the candidates are only READ here -- every rank reorders its own ones in
+// top_split_peer_kernel, after a barrier (a peer may still be scanning them).
+__global__ void __launch_bounds__(kResThreads)
+top_select_peer_kernel(PeerKd pk, TreeGeom g, int cur /* buffer that holds the partitioned records */, int64_t n, int l)
+{
+	__shared__ u32 sh[kBins];
+	__shared__ u32 wsum[32];
+	__shared__ u32 found[3];
+	__shared__ u32 run[2];
+	__shared__ u32 s_minr;
+	__shared__ CandUnion cu;
+	const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	unsigned char *myscr = pk.scr[pk.me];
+	const int node = kd_beg(l) + seg, axis = g.splitdim[node], chain = g.chain[node];
+	const u32 kleft = (u32)(seg_start(n, 2 * (int64_t)seg + 1, l + 1) - seg_start(n, 2 * (int64_t)seg, l + 1));
+	if (tid == 0)
+	{
+		u32 acc = 0, rmin = 0xffffffffu;
+		for (int q = 0; q < pk.world; ++q)
+		{
+			const volatile SegState *sq = scr_seg(pk.scr[q], l) + seg;
+			const volatile int64_t *lbq = scr_range(pk.scr[q], l);
+			cu.base[q] = pk.pay[q][cur] + pk.lo[q] + lbq[seg] + sq->less;
+			cu.pre[q] = acc;
+			acc += sq->eq;
+			const u32 rq = sq->rmin;
+			if (rq < rmin) rmin = rq;
+		}
+		cu.pre[pk.world] = acc;
+		cu.world = pk.world;
+		s_minr = rmin; // global minimum key right of the pivot bin
+		run[0] = 0; run[1] = 0;
+	}
+	__syncthreads();
+	const u32 *gl = scr_glob(myscr, l) + 2 * seg;
+	const u32 eq = cu.pre[pk.world], need = kleft - gl[0]; // 1 <= need <= eq
+	if (tid == 0 && (eq != gl[1] || need < 1u || need > eq))
+	{
+		u32 *dw = kd_dbg(myscr);
+		dw[0] = 100u + (u32)l; dw[1] = (u32)seg; dw[2] = eq; dw[3] = gl[1]; dw[4] = need; dw[5] = kleft; dw[6] = gl[0];
+	}
+
+	// ---- select over the union ----
+	u32 piv[4] = {0u, 0u, 0u, 0u};
+	int depth = 0;
+	u32 r = need - 1, t = eq;
+	for (int d = 0; d < 4; ++d)
+	{
+		if ((d == 1 || d == 2) && ((chain >> (2 * d)) & 3) == kNoAxis) { depth = d + 1; continue; }
+		u32 prefix = 0;
+		for (int pass = 0; pass < 3; ++pass)
+		{
+			const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+			const u32 mask = pass == 2 ? 1023u : 2047u;
+			for (int b = tid; b < kBins; b += kResThreads) sh[b] = 0;
+			__syncthreads();
 			for (u32 i0 = tid; i0 < eq; i0 += 4 * kResThreads)
 			{
-				float4 q[4];
+				float4 q4[4];
 #pragma unroll
-				for (int k = 0; k < 4; ++k) { const u32 i = i0 + k * kResThreads; q[k] = i < eq ? C[i] : make_float4(0.f, 0.f, 0.f, 0.f); }
+				for (int k = 0; k < 4; ++k) { const u32 i = i0 + k * kResThreads; q4[k] = i < eq ? cu.at(i) : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
 				for (int k = 0; k < 4; ++k)
 				{
 					if (i0 + k * kResThreads >= eq) continue;
-					const Words W = words_of(q[k], chain);
+					const Words W = words_of(q4[k], chain);
 					bool m = true;
 					for (int e = 0; e < d; ++e) m = m && W.w[e] == piv[e];
 					if (pass > 0) m = m && (W.w[d] >> (shift + (pass == 1 ? 11 : 10))) == (prefix >> (shift + (pass == 1 ? 11 : 10)));
@@ -351,86 +655,150 @@ top_resolve_kernel(float4 *__restrict__ out, float4 *__restrict__ scratch, TreeG
 		}
 		piv[d] = prefix;
 		depth = d + 1;
-		if (t == 1u || r == t - 1u) break; // the pivot is unique, or every particle that ties with it goes left
+		if (t == 1u || r == t - 1u) break;
 	}
-
-	// ---- split the candidates: lexicographic (w[0 .. depth)) <= piv goes left ----
-	// four rows of kResThreads candidates per trip (independent loads, one pair of barriers per 4096 candidates)
-	__shared__ u32 rowcnt[4][32];
-	if (tid == 0) { run[0] = 0; run[1] = 0; s_minr = 0xffffffffu; }
-	__syncthreads();
+	// ---- smallest key among the union's candidates that go right ----
 	u32 minr = 0xffffffffu;
-	for (u32 base = 0; base < eq; base += 4 * kResThreads)
+	for (u32 i = tid; i < eq; i += kResThreads)
 	{
-		float4 q[4];
-		bool valid[4], left[4];
-		u32 bl[4], br[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-		{
-			const u32 i = base + k * kResThreads + tid;
-			valid[k] = i < eq;
-			q[k] = valid[k] ? C[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-		}
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-		{
-			left[k] = false;
-			if (valid[k])
-			{
-				const Words W = words_of(q[k], chain);
-				left[k] = true; // equal on every compared word: the pivot itself or a tie that goes left
-				for (int e = 0; e < depth; ++e)
-					if (W.w[e] != piv[e]) { left[k] = W.w[e] < piv[e]; break; }
-				if (!left[k]) minr = min(minr, W.w[0]);
-			}
-			bl[k] = __ballot_sync(0xffffffffu, valid[k] && left[k]);
-			br[k] = __ballot_sync(0xffffffffu, valid[k] && !left[k]);
-			if (lane == 0) rowcnt[k][w] = (u32)__popc(bl[k]) | ((u32)__popc(br[k]) << 16);
-		}
-		__syncthreads();
-		u32 ol = run[0], orr = run[1];
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-		{
-			u32 pl = ol, pr = orr;
-			for (int ww = 0; ww < 32; ++ww)
-			{
-				const u32 c = rowcnt[k][ww];
-				if (ww < w) { pl += c & 0xffffu; pr += c >> 16; }
-				ol += c & 0xffffu; orr += c >> 16;
-			}
-			if (valid[k]) T[left[k] ? pl + __popc(bl[k] & ((1u << lane) - 1u)) : need + pr + __popc(br[k] & ((1u << lane) - 1u))] = q[k];
-		}
-		__syncthreads();
-		if (tid == 0) { run[0] = ol; run[1] = orr; }
-		__syncthreads();
+		const Words W = words_of(cu.at(i), chain);
+		bool left = true;
+		for (int e = 0; e < depth; ++e)
+			if (W.w[e] != piv[e]) { left = W.w[e] < piv[e]; break; }
+		if (!left) minr = min(minr, W.w[0]);
 	}
 	minr = __reduce_min_sync(0xffffffffu, minr);
 	if (lane == 0 && minr != 0xffffffffu) atomicMin(&s_minr, minr);
+	__syncthreads();
+	if (tid == 0)
+	{
+		u32 *pv = scr_pivot(myscr, l) + 8 * seg;
+		pv[0] = piv[0]; pv[1] = piv[1]; pv[2] = piv[2]; pv[3] = piv[3]; pv[4] = (u32)depth; pv[5] = s_minr;
+	}
+}
+
+// One CTA per segment: split this rank's own candidates around the pivot (through the other buffer), write the children's
+// boxes and the local range table of the next level
+__global__ void __launch_bounds__(kResThreads)
+top_split_peer_kernel(PeerKd pk, TreeGeom g, int cur, int64_t n, int l)
+{
+	__shared__ u32 wsum[32];
+	__shared__ u32 run[2];
+	const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	unsigned char *myscr = pk.scr[pk.me];
+	const int node = kd_beg(l) + seg, axis = g.splitdim[node], chain = g.chain[node];
+	const u32 *pv = scr_pivot(myscr, l) + 8 * seg;
+	const u32 piv[4] = {pv[0], pv[1], pv[2], pv[3]};
+	const int depth = (int)pv[4];
+	const u32 minr_all = pv[5];
+	if (tid == 0) { run[0] = 0; run[1] = 0; }
+	__syncthreads();
+	// ---- split this rank's own candidates through the other buffer ----
+	const SegState mine = scr_seg(myscr, l)[seg];
+	const int64_t *lbm = scr_range(myscr, l);
+	float4 *C = pk.pay[pk.me][cur] + pk.lo[pk.me] + lbm[seg] + mine.less;
+	float4 *T = pk.pay[pk.me][cur ^ 1] + pk.lo[pk.me] + lbm[seg] + mine.less;
+	const u32 ne = mine.eq;
+	// first pass: how many of the own candidates go left (the right ones are placed behind them)
+	u32 nel = 0;
+	for (u32 i = tid; i < ne; i += kResThreads)
+	{
+		const Words W = words_of(C[i], chain);
+		bool left = true;
+		for (int e = 0; e < depth; ++e)
+			if (W.w[e] != piv[e]) { left = W.w[e] < piv[e]; break; }
+		nel += left ? 1u : 0u;
+	}
+	nel = __reduce_add_sync(0xffffffffu, nel);
+	__syncthreads();
+	if (lane == 0) wsum[w] = nel;
+	__syncthreads();
+	u32 nleft = 0;
+	for (int k = 0; k < 32; ++k) nleft += wsum[k];
+	__syncthreads();
+	for (u32 base = 0; base < ne; base += kResThreads)
+	{
+		const u32 i = base + tid;
+		const bool valid = i < ne;
+		float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+		bool left = false;
+		if (valid)
+		{
+			p = C[i];
+			const Words W = words_of(p, chain);
+			left = true;
+			for (int e = 0; e < depth; ++e)
+				if (W.w[e] != piv[e]) { left = W.w[e] < piv[e]; break; }
+		}
+		const u32 bl = __ballot_sync(0xffffffffu, valid && left), br = __ballot_sync(0xffffffffu, valid && !left);
+		if (lane == 0) wsum[w] = (u32)__popc(bl) | ((u32)__popc(br) << 16);
+		__syncthreads();
+		u32 ol = run[0], orr = run[1];
+		for (int k = 0; k < w; ++k) { ol += wsum[k] & 0xffffu; orr += wsum[k] >> 16; }
+		if (valid) T[left ? ol + __popc(bl & ((1u << lane) - 1u)) : nleft + orr + __popc(br & ((1u << lane) - 1u))] = p;
+		__syncthreads();
+		if (tid == 0)
+		{
+			u32 tl = 0, tr = 0;
+			for (int k = 0; k < 32; ++k) { tl += wsum[k] & 0xffffu; tr += wsum[k] >> 16; }
+			run[0] += tl; run[1] += tr;
+		}
+		__syncthreads();
+	}
 	__threadfence_block();
 	__syncthreads();
-	for (u32 i0 = tid; i0 < eq; i0 += 4 * kResThreads)
-	{
-		float4 q[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) { const u32 i = i0 + k * kResThreads; if (i < eq) q[k] = T[i]; }
-#pragma unroll
-		for (int k = 0; k < 4; ++k) { const u32 i = i0 + k * kResThreads; if (i < eq) C[i] = q[k]; }
-	}
+	for (u32 i = tid; i < ne; i += kResThreads) C[i] = T[i];
 
-	// ---- boxes of the children: cut at the last particle of the left and the first of the right child ----
 	if (tid == 0)
 	{
 		float lb[3], rb[3];
 		for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
-		const int pch = chain;
 		const float save = rb[axis];
 		rb[axis] = unordered_bits(piv[0]);
-		write_box(g, 2*node + 1, lb, rb, pch);
+		write_box(g, 2*node + 1, lb, rb, chain);
 		rb[axis] = save;
-		lb[axis] = unordered_bits(min(s_minr, s.rmin));
-		write_box(g, 2*node + 2, lb, rb, pch);
+		lb[axis] = unordered_bits(minr_all);
+		write_box(g, 2*node + 2, lb, rb, chain);
+		// local ranges of the children
+		u32 *dw = kd_dbg(myscr);
+		dw[20 + 4 * l] = mine.less; dw[21 + 4 * l] = ne; dw[22 + 4 * l] = nleft; dw[23 + 4 * l] = (u32)(lbm[seg + 1] - lbm[seg]);
+		int64_t *nx = scr_range(myscr, l + 1);
+		nx[2 * seg] = lbm[seg];
+		nx[2 * seg + 1] = lbm[seg] + mine.less + nleft;
+		nx[2 * seg + 2] = lbm[seg + 1];
+	}
+}
+
+// after level g - 1 the local records are grouped by destination rank: every rank pulls the pieces of its own subtree
+__global__ void __launch_bounds__(256) exchange_pull_kernel(PeerKd pk, int cur, float4 *__restrict__ dst /* own range of the other buffer */)
+{
+	__shared__ int64_t pre[kMaxPeers + 1];
+	__shared__ const float4 *src[kMaxPeers];
+	if (threadIdx.x == 0)
+	{
+		int64_t acc = 0;
+		for (int q = 0; q < pk.world; ++q)
+		{
+			const volatile int64_t *lbq = scr_range(pk.scr[q], pk.g);
+			src[q] = pk.pay[q][cur] + pk.lo[q] + lbq[pk.me];
+			pre[q] = acc;
+			acc += lbq[pk.me + 1] - lbq[pk.me];
+		}
+		pre[pk.world] = acc;
+	}
+	__syncthreads();
+	const int64_t total = pre[pk.world], stride = (int64_t)gridDim.x * blockDim.x;
+	if (blockIdx.x == 0 && threadIdx.x == 0 && total != pk.lo[pk.me + 1] - pk.lo[pk.me])
+	{
+		u32 *dw = kd_dbg(pk.scr[pk.me]);
+		dw[8] = 200u; dw[9] = (u32)total; dw[10] = (u32)(pk.lo[pk.me + 1] - pk.lo[pk.me]);
+		for (int q = 0; q < pk.world; ++q) dw[11 + q] = (u32)(pre[q + 1] - pre[q]);
+	}
+	for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+	{
+		int q = 0;
+		while (q + 1 < pk.world && t >= pre[q + 1]) ++q;
+		dst[t] = src[q][t - pre[q]];
 	}
 }
 
@@ -813,25 +1181,39 @@ void kd_release(KdTree &t)
 	for (DevBuf *b : all) b->release();
 }
 
-int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom, int r, int g)
+// Load the modules of every kernel of the build NOW (CUDA loads a kernel lazily at its first launch, and that load
+// synchronises the device: if it happens while another rank's flag-barrier kernel spins on the SAME device -- several ranks
+// emulated on one GPU, tests/test_peer_gpu.py -- the ranks wait for each other until the barrier times out).
+int kd_preload_kernels()
+{
+	cudaFuncAttributes fa;
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, bbox_init_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, pack_own_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, pack_bbox_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, root_box_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, root_box_peer_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, top_hist_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, top_pick_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, top_pick_peer_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, top_partition_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, top_resolve_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, top_select_peer_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, top_split_peer_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, exchange_pull_kernel));
+	NBCO_CUDA(cudaFuncGetAttributes(&fa, kd_bottom_kernel));
+	return NBCO_OK;
+}
+
+// levels [l0, lt) of the subtree(s) this rank builds alone, then the shared-memory kernel for the rest
+static int kd_local_levels(nbco_ctx *ctx, KdTree &t, float4 *pay[2], int cur, int l0, cudaEvent_t ev_bottom, int r, int g)
 {
 	cudaStream_t st = ctx->stream;
 	const int64_t n = t.n;
 	TreeGeom tg{t.lbound.as<float>(), t.rbound.as<float>(), t.size2.as<float>(), t.splitdim.as<int>(), t.chain.as<int>()};
-	u32 *bb = t.bbox.as<u32>();
-	static const u32 bb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-	NBCO_CUDA(cudaMemcpyAsync(bb, bb_init, sizeof(bb_init), cudaMemcpyHostToDevice, st));
-	float4 *pay[2] = {t.payA.as<float4>(), t.payB.as<float4>()};
-	pack_bbox_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(pos, pay[0], n, bb);
-	root_box_kernel<<<1, 32, 0, st>>>(tg, bb);
-	ctx->launches += 2;
-
 	u32 *hist = t.hist.as<u32>();
 	SegState *seg = t.seg.as<SegState>();
 	const int ltop = t.lt; // levels [0, ltop) are partitioned globally
-	if (ltop > 0) NBCO_CUDA(cudaMemsetAsync(hist, 0, 4 * (size_t)kBins * ((size_t)1 << (ltop - 1)), st));
-	int cur = 0;
-	for (int l = 0; l < ltop; ++l)
+	for (int l = l0; l < ltop; ++l)
 	{
 		// below level g only the segments of rank r's subtree (multi-GPU: the other subtrees are built by their owners)
 		const int nseg = l >= g ? 1 << (l - g) : 1 << l, seg0 = l >= g ? r << (l - g) : 0;
@@ -864,6 +1246,116 @@ int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom, 
 	++ctx->launches;
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;
+}
+
+int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom, int r, int g)
+{
+	cudaStream_t st = ctx->stream;
+	const int64_t n = t.n;
+	TreeGeom tg{t.lbound.as<float>(), t.rbound.as<float>(), t.size2.as<float>(), t.splitdim.as<int>(), t.chain.as<int>()};
+	u32 *bb = t.bbox.as<u32>();
+	static const u32 bb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+	NBCO_CUDA(cudaMemcpyAsync(bb, bb_init, sizeof(bb_init), cudaMemcpyHostToDevice, st));
+	float4 *pay[2] = {t.payA.as<float4>(), t.payB.as<float4>()};
+	pack_bbox_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, st>>>(pos, pay[0], n, bb);
+	root_box_kernel<<<1, 32, 0, st>>>(tg, bb);
+	ctx->launches += 2;
+	if (t.lt > 0) NBCO_CUDA(cudaMemsetAsync(t.hist.p, 0, 4 * (size_t)kBins * ((size_t)1 << (t.lt - 1)), st));
+	return kd_local_levels(ctx, t, pay, 0, 0, ev_bottom, r, g);
+}
+
+// Distributed build (peer mode, g = log2(world) <= lt): see the section "distributed top levels" above.  pub[q] = the
+// published buffer of rank q as mapped on this device (common.cuh: layout); pos = this rank's array, of which only the own
+// range [lo, hi) is read.  The ranks meet at 3 g + 3 flag barriers (peer_barrier) on their context streams.
+int kd_build_peer(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom, int r, int g, void *const *pub)
+{
+	cudaStream_t st = ctx->stream;
+	const int64_t n = t.n;
+	const int world = 1 << g;
+	static const bool dbg = getenv("NBCO_DEBUG_KD_SYNC") != nullptr; // synchronise and report after every stage
+#define KD_STAGE(name) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(st); fprintf(stderr, "[kd_peer rank %d] %-28s %s\n", r, name, cudaGetErrorString(e_)); } } while (0)
+	if (g < 1 || g > 3 || g > t.lt) { set_error("kd_build_peer: %d ranks for %d global levels", world, t.lt); return NBCO_ERR_INVALID; }
+	TreeGeom tg{t.lbound.as<float>(), t.rbound.as<float>(), t.size2.as<float>(), t.splitdim.as<int>(), t.chain.as<int>()};
+	PeerKd pk;
+	pk.world = world; pk.me = r; pk.g = g;
+	for (int q = 0; q < kMaxPeers; ++q)
+	{
+		unsigned char *base = q < world ? (unsigned char *)pub[q] : nullptr;
+		pk.scr[q] = base ? base + kPeerHeader : nullptr;
+		pk.pay[q][0] = base ? (float4 *)(base + peer_pay_offset(n, 0)) : nullptr;
+		pk.pay[q][1] = base ? (float4 *)(base + peer_pay_offset(n, 1)) : nullptr;
+	}
+	for (int q = 0; q <= world; ++q) pk.lo[q] = seg_start(n, q, g);
+	for (int q = world + 1; q <= kMaxPeers; ++q) pk.lo[q] = n;
+	const int64_t lo = pk.lo[r], cnt = pk.lo[r + 1] - lo;
+	unsigned char *scr = pk.scr[r];
+	float4 *pay[2] = {pk.pay[r][0], pk.pay[r][1]};
+
+	// local histograms of all distributed levels start from zero; local box
+	NBCO_CUDA(cudaMemsetAsync(scr + kScrHist, 0, 4 * (size_t)kBins * ((size_t)world - 1), st));
+	bbox_init_kernel<<<1, 32, 0, st>>>(reinterpret_cast<u32 *>(scr + kScrBBox)); // (device-side: strictly stream ordered)
+	pack_own_kernel<<<grid_for(cnt, 256, ctx->sm_count, 8), 256, 0, st>>>(pos, pay[0], lo, lo + cnt, reinterpret_cast<u32 *>(scr + kScrBBox));
+	++ctx->launches;
+	KD_STAGE("pack_own");
+	NBCO_TRY(peer_barrier(ctx));                       // every local box is published
+	root_box_peer_kernel<<<1, 32, 0, st>>>(tg, pk);
+	++ctx->launches;
+	KD_STAGE("root_box");
+	if (dbg)
+	{
+		for (int q = 0; q < world; ++q)
+		{
+			u32 bbq[6]; long long rg[2];
+			cudaMemcpy(bbq, pk.scr[q] + kScrBBox, sizeof(bbq), cudaMemcpyDeviceToHost);
+			cudaMemcpy(rg, pk.scr[q] + kScrRange, sizeof(rg), cudaMemcpyDeviceToHost);
+			fprintf(stderr, "[kd_peer rank %d] sees rank %d (scr %p): bbox %08x %08x %08x | %08x %08x %08x  range0 %lld %lld\n", r, q, (void *)pk.scr[q],
+			        bbq[0], bbq[1], bbq[2], bbq[3], bbq[4], bbq[5], rg[0], rg[1]);
+		}
+		float rb[6];
+		cudaMemcpy(rb, tg.lbound, 12, cudaMemcpyDeviceToHost); cudaMemcpy(rb + 3, tg.rbound, 12, cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[kd_peer rank %d] root box %g %g %g | %g %g %g\n", r, rb[0], rb[1], rb[2], rb[3], rb[4], rb[5]);
+	}
+	int cur = 0;
+	for (int l = 0; l < g; ++l)
+	{
+		const int nseg = 1 << l;
+		// a local segment holds at most cnt records: tiles sized for that (most tiles of a level find an empty range)
+		int64_t want = (cnt + (int64_t)ctx->sm_count * 4 - 1) / ((int64_t)ctx->sm_count * 4);
+		int64_t tile = ((std::max<int64_t>(want, kChunk) + kChunk - 1) / kChunk) * kChunk;
+		const int tps = (int)((cnt + tile - 1) / tile);
+		const int64_t *lb = reinterpret_cast<const int64_t *>(scr + kScrRange) + 9 * l;
+		u32 *hist = reinterpret_cast<u32 *>(scr + kScrHist) + (size_t)(nseg - 1) * kBins;
+		SegState *seg = reinterpret_cast<SegState *>(scr + kScrSeg) + 8 * l;
+		top_hist_kernel<<<nseg * tps, kTopThreads, 0, st>>>(pay[cur], tg, hist, n, l, tps, (int)tile, 0, lb, lo);
+		++ctx->launches;
+		KD_STAGE("hist");
+		NBCO_TRY(peer_barrier(ctx));                   // every local histogram of this level is published
+		top_pick_peer_kernel<<<nseg, 256, 0, st>>>(pk, n, l);
+		KD_STAGE("pick");
+		top_partition_kernel<<<nseg * tps, kTopThreads, 0, st>>>(pay[cur], pay[cur ^ 1], tg, seg, n, l, tps, (int)tile, 0, lb, lo);
+		ctx->launches += 2;
+		KD_STAGE("partition");
+		NBCO_TRY(peer_barrier(ctx));                   // every rank's candidates and local minima are in place
+		top_select_peer_kernel<<<nseg, kResThreads, 0, st>>>(pk, tg, cur ^ 1, n, l);
+		++ctx->launches;
+		KD_STAGE("select");
+		NBCO_TRY(peer_barrier(ctx));                   // nobody scans this rank's candidates any more: they may be reordered
+		top_split_peer_kernel<<<nseg, kResThreads, 0, st>>>(pk, tg, cur ^ 1, n, l);
+		++ctx->launches;
+		KD_STAGE("split");
+		cur ^= 1;
+	}
+	NBCO_TRY(peer_barrier(ctx));                       // every rank's records are grouped by destination, tables published
+	exchange_pull_kernel<<<grid_for(cnt, 256, ctx->sm_count, 8), 256, 0, st>>>(pk, cur, pay[cur ^ 1] + lo);
+	++ctx->launches;
+	KD_STAGE("exchange");
+	cur ^= 1;
+	NBCO_TRY(peer_barrier(ctx));                       // nobody reads this rank's records any more: the local levels may overwrite them
+	if (t.lt > g) NBCO_CUDA(cudaMemsetAsync(t.hist.p, 0, 4 * (size_t)kBins * ((size_t)1 << (t.lt - 1 - g)), st));
+	const int rc = kd_local_levels(ctx, t, pay, cur, g, ev_bottom, r, g);
+	KD_STAGE("local levels + bottom");
+#undef KD_STAGE
+	return rc;
 }
 
 } // namespace nbco

@@ -12,6 +12,7 @@
 // The 64-byte IPC handles travel between the processes through torch.distributed (parallel.py).
 
 #include "common.cuh"
+#include "fmm3_common.cuh"
 
 namespace nbco {
 
@@ -21,7 +22,7 @@ struct BarrierArgs { unsigned long long *flags[kPeerMax]; int world, me; };
 
 // every rank writes `epoch` into slot [me] of every rank's flag array, then waits until all slots of its own
 // array reached `epoch`.  Bounded spin: a rank that never arrives raises err instead of hanging the GPU.
-__global__ void peer_barrier_kernel(BarrierArgs a, unsigned long long epoch, unsigned *err, long long timeout_cycles)
+__global__ void peer_barrier_kernel(BarrierArgs a, unsigned long long epoch, unsigned *err, long long timeout_cycles, unsigned long long *dbg)
 {
 	const int q = threadIdx.x;
 	__threadfence_system();
@@ -35,11 +36,14 @@ __global__ void peer_barrier_kernel(BarrierArgs a, unsigned long long epoch, uns
 	{
 		volatile unsigned long long *src = a.flags[a.me] + q;
 		const long long t0 = clock64();
+		unsigned long long spins = 0;
 		while (*src < epoch)
 		{
 			if (clock64() - t0 > timeout_cycles) { *err = 1u; break; }
 			__nanosleep(100);
+			++spins;
 		}
+		if (dbg) { dbg[4 * q] = epoch; dbg[4 * q + 1] = spins; dbg[4 * q + 2] = *src; dbg[4 * q + 3] = (unsigned long long)(clock64() - t0); }
 	}
 	__threadfence_system();
 }
@@ -65,13 +69,24 @@ int peer_barrier(nbco_ctx *ctx)
 		if (!(sec > 0.0)) sec = 30.0;
 		timeout_cycles = (long long)(sec * 2.0e9);
 	}
-	peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(a, ++ps.epoch, err, timeout_cycles);
+	static const bool debug = getenv("NBCO_DEBUG_KD_SYNC") != nullptr;
+	unsigned long long *dbg = debug ? (unsigned long long *)((char *)ps.pub.p + 640) : nullptr; // 4 words per peer, inside the header
+	peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(a, ++ps.epoch, err, timeout_cycles, dbg);
+	if (debug)
+	{
+		unsigned long long h[4 * kPeerMax]; unsigned e = 0;
+		cudaStreamSynchronize(ctx->stream);
+		cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost); cudaMemcpy(&e, err, 4, cudaMemcpyDeviceToHost);
+		for (int q = 0; q < ps.world; ++q)
+			fprintf(stderr, "[barrier rank %d] epoch %llu waited on rank %d: spins %llu, flag %llu, cycles %llu, err %u, timeout %lld\n", ps.me,
+			        h[4*q], q, h[4*q+1], h[4*q+2], h[4*q+3], e, timeout_cycles);
+	}
 	++ctx->launches;
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;
 }
 
-static float *mirror(void *pub, int which, int64_t n) { return (float *)((char *)pub + kPeerHeader) + (size_t)which * 3 * (size_t)n; }
+static float *mirror(void *pub, int which, int64_t n) { return (float *)((char *)pub + kPeerData) + (size_t)which * 3 * (size_t)n; }
 
 int peer_publish(nbco_ctx *ctx, const float *d_full, int which, int64_t n)
 {
@@ -141,8 +156,13 @@ int nbco_peer_export(nbco_ctx *ctx, int64_t n, void *h_handles)
 	if (ps.active) { set_error("peers already attached"); return NBCO_ERR_INVALID; }
 	void *center = nullptr, *mpole = nullptr;
 	NBCO_TRY(fmm3_peer_buffers(ctx, n, &center, &mpole));
-	NBCO_TRY(ps.pub.reserve(kPeerHeader + 24 * (size_t)n));
-	NBCO_CUDA(cudaMemsetAsync(ps.pub.p, 0, kPeerHeader, ctx->stream));
+	{
+		cudaFuncAttributes fa; // see kd_preload_kernels(): no lazy module load while a barrier kernel spins
+		NBCO_CUDA(cudaFuncGetAttributes(&fa, peer_barrier_kernel));
+		NBCO_TRY(kd_preload_kernels());
+	}
+	NBCO_TRY(ps.pub.reserve(peer_pub_bytes(n)));
+	NBCO_CUDA(cudaMemsetAsync(ps.pub.p, 0, kPeerData, ctx->stream));
 	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
 	ps.world = w; ps.me = ctx->cfg.rank; ps.n = n; ps.epoch = 0; ps.have_full = true;
 	ps.center[ps.me] = center; ps.mpole[ps.me] = mpole; ps.pubp[ps.me] = ps.pub.p;
