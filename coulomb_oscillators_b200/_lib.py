@@ -42,7 +42,7 @@ SYMBOLS = [
     "nbco_default_config", "nbco_abi_version", "nbco_last_error", "nbco_create", "nbco_destroy",
     "nbco_set_config", "nbco_get_config", "nbco_stream", "nbco_force_direct3", "nbco_force_fmm3_kd",
     "nbco_coulomb_direct3", "nbco_coulomb_fmm3_kd", "nbco_add_elastic", "nbco_step", "nbco_compute_force",
-    "nbco_integrate", "nbco_mean_rel_err", "nbco_energy", "nbco_eval_host", "nbco_run_host", "nbco_step_host",
+    "nbco_integrate", "nbco_integrate_energy", "nbco_mean_rel_err", "nbco_energy", "nbco_eval_host", "nbco_run_host", "nbco_step_host",
     "nbco_fmm_get_info", "nbco_fmm_get_tree", "nbco_fmm_get_lists", "nbco_fmm_get_phase_ms", "nbco_fmm_phase_totals",
     "nbco_force_direct2", "nbco_force_fmm2", "nbco_coulomb_direct2", "nbco_coulomb_fmm2", "nbco_add_elastic2", "nbco_step2",
     "nbco_compute_force2", "nbco_integrate2", "nbco_mean_rel_err2", "nbco_energy2", "nbco_run_host2", "nbco_step_host2",
@@ -75,6 +75,7 @@ def _load():
     L.nbco_step.argtypes = [vp, vp, vp, f32, i64]
     L.nbco_compute_force.argtypes = [vp, C.c_int, vp, i64, vp]
     L.nbco_integrate.argtypes = [vp, C.c_int, C.c_int, vp, i64, vp, f64, i64]
+    L.nbco_integrate_energy.argtypes = [vp, C.c_int, C.c_int, vp, i64, vp, f64, i64, C.POINTER(f64)]
     L.nbco_mean_rel_err.argtypes = [vp, vp, vp, i64, C.POINTER(f64), C.POINTER(f64)]
     L.nbco_energy.argtypes = [vp, vp, i64, vp, C.POINTER(f64)]
     L.nbco_eval_host.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp]
@@ -271,6 +272,12 @@ class Context:
 
     def integrate(self, scheme, evaluator, d_buf, n, d_param, dt, nsteps):
         _check(lib.nbco_integrate(self._h, scheme, evaluator, d_buf, n, d_param, dt, nsteps))
+
+    def integrate_energy(self, scheme, evaluator, d_buf, n, d_param, dt, nsteps):
+        """nbco_integrate with the last update fused with the energy reduction: returns (kinetic, elastic) of the final state"""
+        out = (C.c_double * 2)()
+        _check(lib.nbco_integrate_energy(self._h, scheme, evaluator, d_buf, n, d_param, dt, nsteps, out))
+        return out[0], out[1]
 
     def mean_rel_err(self, d_a, d_ref, n):
         m, x = C.c_double(), C.c_double()

@@ -85,24 +85,33 @@ static int sync(nbco_ctx *ctx)
 
 // One step of a scheme, enqueued on the context stream (no host synchronisation inside).
 // [lo, hi): the particles this context advances (peer mode: the rank's own tree-order range; else everything)
-static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64_t n, const float *param, float dtf, int64_t lo, int64_t hi)
+// d_energy != nullptr: the LAST update of the step (a kick for leapfrog, a drift for Forest-Ruth / PEFRL) also accumulates the
+// kinetic and elastic energy of the state it produces (step_energy_launch); Euler ends with the force evaluation, its last
+// update is the drift
+static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64_t n, const float *param, float dtf, int64_t lo, int64_t hi,
+                       double *d_energy = nullptr)
 {
 	float *pos = buf, *vel = buf + 3*n, *acc = buf + 6*n;
 	const long double dt = dtf, ds = dt * 1.0L; // scale = 1 everywhere in the reference
-	auto K = [&](long double c) { return step_launch(ctx, vel + 3*lo, acc + 3*lo, (float)c, hi - lo); };
-	auto D = [&](long double c)
+	auto K = [&](long double c, bool last = false)
+	{
+		if (last && d_energy) return step_energy_launch(ctx, vel + 3*lo, acc + 3*lo, (float)c, pos + 3*lo, true, param, hi - lo, d_energy);
+		return step_launch(ctx, vel + 3*lo, acc + 3*lo, (float)c, hi - lo);
+	};
+	auto D = [&](long double c, bool last = false)
 	{
 		if (ctx->peer.active) ctx->peer.have_full = false; // the other ranges of this rank's arrays are stale from here on
+		if (last && d_energy) return step_energy_launch(ctx, pos + 3*lo, vel + 3*lo, (float)c, nullptr, false, param, hi - lo, d_energy);
 		return step_launch(ctx, pos + 3*lo, vel + 3*lo, (float)c, hi - lo);
 	};
 	auto F = [&]() { return eval_dispatch(ctx, evaluator, pos, acc, n, param); };
 	switch (scheme)
 	{
 		case NBCO_EULER: // integrator.cuh:32-48
-			NBCO_TRY(K(ds)); NBCO_TRY(D(dt)); NBCO_TRY(F());
+			NBCO_TRY(K(ds)); NBCO_TRY(D(dt, true)); NBCO_TRY(F());
 			return NBCO_OK;
 		case NBCO_LEAPFROG: // integrator.cuh:68-96
-			NBCO_TRY(K(ds * 0.5L)); NBCO_TRY(D(dt)); NBCO_TRY(F()); NBCO_TRY(K(ds * 0.5L));
+			NBCO_TRY(K(ds * 0.5L)); NBCO_TRY(D(dt)); NBCO_TRY(F()); NBCO_TRY(K(ds * 0.5L, true));
 			return NBCO_OK;
 		case NBCO_FORESTRUTH: // integrator.cuh:98-128
 		{
@@ -110,7 +119,7 @@ static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int
 			NBCO_TRY(D(dt * th / 2)); NBCO_TRY(F());
 			NBCO_TRY(K(ds * th)); NBCO_TRY(D(dt * (1 - th) / 2)); NBCO_TRY(F());
 			NBCO_TRY(K(ds * (1 - 2*th))); NBCO_TRY(D(dt * (1 - th) / 2)); NBCO_TRY(F());
-			NBCO_TRY(K(ds * th)); NBCO_TRY(D(dt * th / 2));
+			NBCO_TRY(K(ds * th)); NBCO_TRY(D(dt * th / 2, true));
 			return NBCO_OK;
 		}
 		case NBCO_PEFRL: // integrator.cuh:130-167
@@ -120,7 +129,7 @@ static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int
 			NBCO_TRY(K(ds * (1 - 2*la) / 2)); NBCO_TRY(D(dt * ch)); NBCO_TRY(F());
 			NBCO_TRY(K(ds * la)); NBCO_TRY(D(dt * (1 - 2*(ch + xi)))); NBCO_TRY(F());
 			NBCO_TRY(K(ds * la)); NBCO_TRY(D(dt * ch)); NBCO_TRY(F());
-			NBCO_TRY(K(ds * (1 - 2*la) / 2)); NBCO_TRY(D(dt * xi));
+			NBCO_TRY(K(ds * (1 - 2*la) / 2)); NBCO_TRY(D(dt * xi, true));
 			return NBCO_OK;
 		}
 		default:
@@ -132,7 +141,7 @@ static int scheme_step(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int
 // nsteps steps of a scheme.  Leapfrog runs fused: K(1/2) D | F | [K(1/2) K(1/2) D | F]* | K(1/2) -- the
 // same fma sequence per element as integrator.cuh:68-96 applied step by step, in fewer passes.
 static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64_t n, const float *param, float dtf, int64_t nsteps,
-                     cudaEvent_t ev_last_drift = nullptr)
+                     cudaEvent_t ev_last_drift = nullptr, double *d_energy = nullptr)
 {
 	// peer mode (peer.cu): every rank steps its own tree-order range; the evaluator exchanges what it needs
 	int64_t lo = 0, hi = n;
@@ -141,7 +150,7 @@ static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64
 	if (scheme != NBCO_LEAPFROG || nsteps <= 0)
 	{
 		for (int64_t s = 0; s < nsteps; ++s)
-			NBCO_TRY(scheme_step(ctx, scheme, evaluator, buf, n, param, dtf, lo, hi));
+			NBCO_TRY(scheme_step(ctx, scheme, evaluator, buf, n, param, dtf, lo, hi, s + 1 == nsteps ? d_energy : nullptr));
 		return NBCO_OK;
 	}
 	float *pos = buf, *vel = buf + 3*n, *acc = buf + 6*n;
@@ -157,6 +166,7 @@ static int run_steps(nbco_ctx *ctx, int scheme, int evaluator, float *buf, int64
 		NBCO_TRY(eval_dispatch(ctx, evaluator, pos, acc, n, param));
 	}
 	if (ctx->peer.active) ctx->peer.have_full = false;
+	if (d_energy) return step_energy_launch(ctx, vel + 3*lo, acc + 3*lo, h, pos + 3*lo, true, param, hi - lo, d_energy);
 	return step_launch(ctx, vel + 3*lo, acc + 3*lo, h, hi - lo);
 }
 
@@ -320,6 +330,19 @@ int nbco_integrate(nbco_ctx *ctx, int scheme, int evaluator, void *d_buf, int64_
 	ENTER(ctx);
 	const float dtf = (float)dt; // main3.cu:231
 	NBCO_TRY(run_steps(ctx, scheme, evaluator, (float *)d_buf, n, (const float *)d_param, dtf, nsteps));
+	return sync(ctx);
+}
+
+int nbco_integrate_energy(nbco_ctx *ctx, int scheme, int evaluator, void *d_buf, int64_t n,
+                          const void *d_param, double dt, int64_t nsteps, double *h_kin_el)
+{
+	ENTER(ctx);
+	if (!h_kin_el || nsteps < 1) { set_error("nbco_integrate_energy: needs an output and at least one step"); return NBCO_ERR_INVALID; }
+	NBCO_TRY(ctx->red.reserve(4 * sizeof(double)));
+	double *d = ctx->red.as<double>();
+	NBCO_CUDA(cudaMemsetAsync(d, 0, 2 * sizeof(double), ctx->stream));
+	NBCO_TRY(run_steps(ctx, scheme, evaluator, (float *)d_buf, n, (const float *)d_param, (float)dt, nsteps, nullptr, d));
+	NBCO_CUDA(cudaMemcpyAsync(h_kin_el, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	return sync(ctx);
 }
 

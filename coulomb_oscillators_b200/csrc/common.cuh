@@ -102,6 +102,9 @@ int pair_energy_launch(nbco_ctx *ctx, const float *d_pos, int64_t n, double *d_o
 // integrate.cu
 int add_elastic_launch(nbco_ctx *ctx, const float *d_pos, float *d_acc, int64_t n, const float *d_k3);
 int step_launch(nbco_ctx *ctx, float *d_b, const float *d_a, float ds, int64_t n);
+// the same update fused with the kinetic / elastic energy sums of the state it produces (d_out2: two doubles, accumulated)
+int step_energy_launch(nbco_ctx *ctx, float *d_b, const float *d_a, float ds, const float *d_other, bool b_is_vel,
+                       const float *d_param, int64_t n, double *d_out2);
 int kick_drift_launch(nbco_ctx *ctx, float *d_pos, float *d_vel, const float *d_acc, float k1, float k2, bool two, float dt, int64_t n);
 int rel_err_launch(nbco_ctx *ctx, const float *d_a, const float *d_ref, int64_t n, double *h_mean, double *h_max);
 int kinetic_elastic_launch(nbco_ctx *ctx, const float *d_buf, int64_t n, const float *d_param, double *h_out2);

@@ -163,7 +163,43 @@ __global__ void __launch_bounds__(kBlock) kin_el_kernel(const float *__restrict_
 	if (threadIdx.x == 0) { atomicAdd(out, ke); atomicAdd(out + 1, el); }
 }
 
+// The LAST update of an integration fused with the energy reduction (north star: "fused integrator kick/drift plus the
+// energy reduction"): b = fma(ds, a, b) exactly like axpy_kernel, and in the same pass out[0] += sum 1/2 v^2,
+// out[1] += 1/2 sum k o x^2 of the state just produced.  b_is_vel: the update is a kick (b = velocities, a =
+// accelerations, other = positions); else a drift (b = positions, a = velocities; other unused).
+__global__ void __launch_bounds__(kBlock)
+axpy_energy_kernel(float *__restrict__ b, const float *__restrict__ a, float ds, const float *__restrict__ other, int b_is_vel,
+                   const float *__restrict__ param, int64_t m, double *__restrict__ out)
+{
+	__shared__ double sh[32];
+	double ke = 0.0, el = 0.0;
+	float k[3] = {1.f, 1.f, 1.f};
+	if (param) { k[0] = param[3]; k[1] = param[4]; k[2] = param[5]; }
+	const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
+	{
+		const float nb = fmaf(ds, a[i], b[i]);
+		b[i] = nb;
+		const double v = b_is_vel ? (double)nb : (double)a[i], x = b_is_vel ? (double)other[i] : (double)nb;
+		ke += 0.5 * v * v;
+		el += 0.5 * (double)k[i % 3] * x * x;
+	}
+	ke = block_sum(ke, sh);
+	el = block_sum(el, sh);
+	if (threadIdx.x == 0) { atomicAdd(out, ke); atomicAdd(out + 1, el); }
+}
+
 } // namespace
+
+int step_energy_launch(nbco_ctx *ctx, float *d_b, const float *d_a, float ds, const float *d_other, bool b_is_vel,
+                       const float *d_param, int64_t n, double *d_out2)
+{
+	if (n <= 0) return NBCO_OK;
+	axpy_energy_kernel<<<grid_for(3 * n, kBlock, ctx->sm_count, 8), kBlock, 0, ctx->stream>>>(d_b, d_a, ds, d_other, b_is_vel ? 1 : 0, d_param, 3 * n, d_out2);
+	++ctx->launches;
+	NBCO_CUDA(cudaGetLastError());
+	return NBCO_OK;
+}
 
 int step_launch(nbco_ctx *ctx, float *d_b, const float *d_a, float ds, int64_t n)
 {

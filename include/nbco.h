@@ -118,6 +118,13 @@ int nbco_compute_force(nbco_ctx *ctx, int evaluator, void *d_buf, int64_t n, con
 int nbco_integrate(nbco_ctx *ctx, int scheme, int evaluator, void *d_buf, int64_t n,
                    const void *d_param, double dt, int64_t nsteps);
 
+/* nbco_integrate whose LAST update (the closing kick of leapfrog, the closing drift of the other schemes) is fused with the
+ * energy reduction: h_kin_el[0] = sum 1/2 v^2, h_kin_el[1] = 1/2 sum k o x^2 of the final state, accumulated in double in the
+ * same pass that writes it (no extra sweep over the state).  Peer mode: the sums cover the rank's own range.  (Euler ends
+ * with a force evaluation: its energies belong to the state after the drift, i.e. the final positions and velocities.) */
+int nbco_integrate_energy(nbco_ctx *ctx, int scheme, int evaluator, void *d_buf, int64_t n,
+                          const void *d_param, double dt, int64_t nsteps, double *h_kin_el);
+
 /* ---- diagnostics ---- */
 /* mean over i of |a-ref| / sqrt(|ref|^2 + 1e-18) (rel_diff1, reductions.cuh:37-42; the index
  * bug of relerrReduce2 :89 is not reproduced).  Result on the host. */

@@ -26,7 +26,7 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_defaults():
     import coulomb_oscillators_b200 as nb
-    assert nb.lib.nbco_abi_version() == 2
+    assert nb.lib.nbco_abi_version() == 3
     cfg = nb._lib.default_config()
     # defaults of reference constants.cuh:36-52
     assert (cfg.order, cfg.tree_steps, cfg.coll, cfg.unsort, cfg.max_level) == (3, 8, 1, 1, 0)

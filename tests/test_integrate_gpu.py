@@ -134,3 +134,28 @@ def test_step_host_matches_device_integration(evaluator):
         g = np.lexsort((got[0][:, 2], got[0][:, 1], got[0][:, 0]))
         assert np.abs(got[0][g] - want[0][o]).max() <= 1e-6 * np.abs(want[0]).max()
         assert np.abs(got[1][g] - want[1][o]).max() <= 1e-5 * np.abs(want[1]).max()
+
+
+@pytest.mark.parametrize("scheme", [nb.EULER, nb.LEAPFROG, nb.FORESTRUTH, nb.PEFRL])
+def test_fused_energy_reduction_matches_the_separate_pass(scheme):
+    """nbco_integrate_energy: the last kick / drift of the integration also reduces 1/2 v^2 and 1/2 k x^2 of the state it
+    writes; same state bits as nbco_integrate, same sums as the separate nbco_energy pass (double accumulation)"""
+    import torch
+    n, steps = 30000, 3
+    st = nb.init_ga(n)
+    par = torch.from_numpy(nb.default_param(n)).cuda()
+    ev = nb.EVAL_COULOMB_DIRECT3          # deterministic evaluator: the two runs must agree bit for bit
+    bufs = []
+    for fused in (0, 1):
+        c = nb.Context()
+        b = torch.zeros(9 * n, dtype=torch.float32, device="cuda")
+        b[:6 * n] = torch.from_numpy(st.ravel()).cuda()
+        c.compute_force(ev, b.data_ptr(), n, par.data_ptr())
+        if fused:
+            ke, el = c.integrate_energy(scheme, ev, b.data_ptr(), n, par.data_ptr(), 5e-4, steps)
+        else:
+            c.integrate(scheme, ev, b.data_ptr(), n, par.data_ptr(), 5e-4, steps)
+        bufs.append(b)
+    assert torch.equal(bufs[0][:6 * n], bufs[1][:6 * n])
+    e = nb.Context().energy(bufs[1].data_ptr(), n, par.data_ptr())
+    assert abs(ke - e[0]) <= 1e-12 * abs(e[0]) and abs(el - e[1]) <= 1e-12 * abs(e[1])
