@@ -906,6 +906,7 @@ struct FmmPlan
 	int64_t n = 0;
 	int L = 0, ntot = 0, order = 0, offM = 0, offL = 0, sM = 0, sL = 0, mlt_max = 0;
 	int counter = 0, rebuilt = 0, max_level = -1;
+	int leaf_pending = 0; // the last downward pass may have kept the leaf level of the L2L pass in registers (OrderOps::finish_leaf_locals)
 	float dens = 0.f;
 	int64_t p2p_n = 0, m2l_n = 0;
 	u32 cap_list = 0, cap_front = 0;
@@ -1284,6 +1285,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 		const CsrView cv{ca.off, ca.src, p.ntot, p.cap_src};
 		ops.downward(ctx, t, spos, nullptr, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll,
 		             p.ev[PH_L2P], &cv);
+		p.leaf_pending = 0;
 	}
 	else
 	{
@@ -1310,6 +1312,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_L2L], st));
 	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll,
 	             p.ev[PH_L2P], nullptr);
+	p.leaf_pending = 1;
 	}
 	if (peer) NBCO_TRY(peer_barrier(ctx)); // nobody reads this rank's centres / multipoles / positions any more
 	eval_check_kernel<<<1, 32, 0, st>>>(a.cnt, p.cap_list); LAUNCHED(ctx);
@@ -1506,6 +1509,14 @@ int nbco_fmm_get_tree(nbco_ctx *ctx, float *h_center, float *h_lbound, float *h_
 	NBCO_CUDA(cudaSetDevice(ctx->cfg.device));
 	FmmPlan &p = *ctx->fmm;
 	const size_t nt = (size_t)p.ntot;
+	if (h_local && p.leaf_pending)
+	{
+		const OrderOps *ops = order_ops(p.order);
+		int g = 0; while ((1 << g) < ctx->cfg.world) ++g;
+		TreeData t{p.center.as<float4>(), p.kd.size2.as<float>(), p.mpole.as<float>(), p.local.as<float>(), p.sM, p.sL, {}};
+		if (ops && ops->finish_leaf_locals) ops->finish_leaf_locals(ctx, t, p.n, p.L, ctx->cfg.world > 1 ? ctx->cfg.rank : 0, ctx->cfg.world > 1 ? g : 0);
+		p.leaf_pending = 0;
+	}
 	NBCO_CUDA(cudaStreamSynchronize(ctx->stream));
 	if (h_lbound) NBCO_CUDA(cudaMemcpy(h_lbound, p.kd.lbound.p, 12 * nt, cudaMemcpyDeviceToHost));
 	if (h_rbound) NBCO_CUDA(cudaMemcpy(h_rbound, p.kd.rbound.p, 12 * nt, cudaMemcpyDeviceToHost));

@@ -11,8 +11,15 @@ typedef unsigned long long u64;
 typedef unsigned int u32;
 typedef unsigned short u16;
 
-constexpr int kBottomCap = 8192;   // particles a bottom CTA keeps in shared memory
-constexpr int kBottomThreads = 1024;
+#ifndef NBCO_BOTTOM_CAP
+#define NBCO_BOTTOM_CAP 8192
+#endif
+#ifndef NBCO_BOTTOM_THREADS
+#define NBCO_BOTTOM_THREADS 1024
+#endif
+constexpr int kBottomCap = NBCO_BOTTOM_CAP;   // particles a bottom CTA keeps in shared memory (22 bytes each + block state)
+constexpr int kBottomThreads = NBCO_BOTTOM_THREADS;
+constexpr int kBottomCtasPerSm = kBottomCap <= 4096 && kBottomThreads <= 512 ? 2 : 1; // two resident CTAs need <= 64 registers and half the memory
 constexpr int kNoAxis = 3;
 constexpr int kFlagShift = 28;             // interaction-list entries carry two target flags above the node id
 constexpr int kNodeMask = (1 << kFlagShift) - 1;
@@ -213,6 +220,9 @@ struct OrderOps
 	                 float eps2, int coll, cudaEvent_t ev_l2p /* recorded between the L2L levels and the L2P kernel */,
 	                 const CsrView *csr);
 	int by_target;   // 1: the passes of this order implement the by-target flow
+	// pair-list flow: downward() may leave the leaf level of the L2L pass to its L2P kernel (locals of the leaves then hold
+	// the M2L sums only); this pushes that level for callers that read the tuples back.  nullptr: never fused
+	void (*finish_leaf_locals)(nbco_ctx *ctx, TreeData t, int64_t n, int L, int r, int g);
 };
 const OrderOps *order_ops(int order);
 

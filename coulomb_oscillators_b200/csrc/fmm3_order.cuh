@@ -614,6 +614,113 @@ l2p_uniform_kernel(TreeData t, const float *__restrict__ spos, const float *__re
 	}
 }
 
+// L2L of the LEAF level fused into L2P (uniform leaves of C particles, tuples of 16 floats, P <= 3): FOUR lanes per leaf.
+// Each lane moves one float4 of the parent's and of the leaf's tuple (as l2l_level4_kernel), the four shift the parent's
+// expansion to the leaf's centre in registers and every lane evaluates C / 4 of the leaf's particles.  The leaf's final
+// tuple is never written: against the two-kernel form this saves one 64-byte write and one 64-byte read per leaf and
+// three of every four expansions of the same tuple (nbco_fmm_get_tree finishes the leaf level on demand,
+// finish_leaf_locals below).  Same operations in the same order as l2l_level4_kernel + l2p_uniform_kernel: bit-identical.
+template <int P, int C>
+__global__ void __launch_bounds__(128)
+l2lp_uniform_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__ acc_near, float *__restrict__ acc_out,
+                    const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int L, int leaf_lo, int leaf_hi, float eps2, int coll)
+{
+	static_assert(pad4<trl_off(P + 1)>() == 16 && C % 4 == 0, "four float4 per tuple, C / 4 particles per lane");
+	constexpr int K = C / 4; // particles per lane
+	const float scale = param ? param[0] : 1.f;
+	float k3[3] = {1.f, 1.f, 1.f};
+	if (fuse_elastic && param) { k3[0] = param[3]; k3[1] = param[4]; k3[2] = param[5]; }
+	const int beg = kd_beg(L);
+	const int sub = threadIdx.x & 3;
+	const unsigned gmask = 0xFu << ((threadIdx.x & 31) & ~3);
+	const int stride = (int)((gridDim.x * blockDim.x) >> 2);
+	for (int leaf = leaf_lo + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 2); leaf < leaf_hi; leaf += stride) // a group of four stays together
+	{
+		const int child = beg + leaf, parent = (child - 1) >> 1;
+		const float4 qp = reinterpret_cast<const float4 *>(t.local + (int64_t)parent * t.sL)[sub];
+		const float4 qc = reinterpret_cast<const float4 *>(t.local + (int64_t)child * t.sL)[sub];
+		const float4 cp = t.center[parent], cc = t.center[child];
+		// my K particles: 3 K consecutive floats of the leaf's row
+		const int64_t j0 = (int64_t)leaf * C + sub * K;
+		float tp[3 * K], an[3 * K];
+		{
+			const float2 *p2 = reinterpret_cast<const float2 *>(spos + 3 * j0), *a2 = reinterpret_cast<const float2 *>(acc_near + 3 * j0);
+#pragma unroll
+			for (int m = 0; m < 3 * K / 2; ++m) { const float2 v = p2[m], w = a2[m]; tp[2*m] = v.x; tp[2*m+1] = v.y; an[2*m] = w.x; an[2*m+1] = w.y; }
+		}
+		float Lp[16], Lc[16], S[sym_off(P + 1)];
+#pragma unroll
+		for (int q = 0; q < 4; ++q)
+		{
+			Lp[4*q]   = __shfl_sync(gmask, qp.x, q, 4); Lp[4*q+1] = __shfl_sync(gmask, qp.y, q, 4);
+			Lp[4*q+2] = __shfl_sync(gmask, qp.z, q, 4); Lp[4*q+3] = __shfl_sync(gmask, qp.w, q, 4);
+			Lc[4*q]   = __shfl_sync(gmask, qc.x, q, 4); Lc[4*q+1] = __shfl_sync(gmask, qc.y, q, 4);
+			Lc[4*q+2] = __shfl_sync(gmask, qc.z, q, 4); Lc[4*q+3] = __shfl_sync(gmask, qc.w, q, 4);
+		}
+		S[0] = 0.f;
+		local_expand<P>(S, Lp);
+		l2l_acc<P>(Lc, S, cc.x - cp.x, cc.y - cp.y, cc.z - cp.z);
+		S[0] = 0.f;
+		local_expand<P>(S, Lc);
+		float f[K][3];
+#pragma unroll
+		for (int k = 0; k < K; ++k) l2p_field<P>(f[k], S, tp[3*k] - cc.x, tp[3*k+1] - cc.y, tp[3*k+2] - cc.z);
+		if (coll)
+		{
+			float a[K][3];
+#pragma unroll
+			for (int k = 0; k < K; ++k) a[k][0] = a[k][1] = a[k][2] = 0.f;
+			const float4 *src = reinterpret_cast<const float4 *>(spos + 3 * (int64_t)leaf * C);
+#pragma unroll
+			for (int q = 0; q < C / 4; ++q)
+			{
+				const float4 v0 = src[3*q], v1 = src[3*q+1], v2 = src[3*q+2];
+				const float sx[4] = {v0.x, v0.w, v1.z, v2.y}, sy[4] = {v0.y, v1.x, v1.w, v2.z}, sz[4] = {v0.z, v1.y, v2.x, v2.w};
+#pragma unroll
+				for (int s = 0; s < 4; ++s)
+#pragma unroll
+					for (int k = 0; k < K; ++k)
+					{
+						const float dx = tp[3*k] - sx[s], dy = tp[3*k+1] - sy[s], dz = tp[3*k+2] - sz[s];
+						float r2 = fmaf(dx, dx, eps2);
+						r2 = fmaf(dy, dy, r2);
+						r2 = fmaf(dz, dz, r2);
+						float w;
+						asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(r2));
+						w = w * fmaf(-0.5f * r2 * w, w, 1.5f);
+						const float w3 = (w * w) * w;
+						a[k][0] = fmaf(dx, w3, a[k][0]); a[k][1] = fmaf(dy, w3, a[k][1]); a[k][2] = fmaf(dz, w3, a[k][2]);
+					}
+			}
+#pragma unroll
+			for (int k = 0; k < K; ++k) { f[k][0] += a[k][0]; f[k][1] += a[k][1]; f[k][2] += a[k][2]; }
+		}
+		float o3[3 * K];
+#pragma unroll
+		for (int k = 0; k < K; ++k)
+		{
+			float ax = (an[3*k] + f[k][0]) * scale, ay = (an[3*k+1] + f[k][1]) * scale, az = (an[3*k+2] + f[k][2]) * scale;
+			if (fuse_elastic) { ax = fmaf(-k3[0], tp[3*k], ax); ay = fmaf(-k3[1], tp[3*k+1], ay); az = fmaf(-k3[2], tp[3*k+2], az); }
+			o3[3*k] = ax; o3[3*k+1] = ay; o3[3*k+2] = az;
+		}
+		if (perm_or_null)
+		{
+#pragma unroll
+			for (int k = 0; k < K; ++k)
+			{
+				const int64_t o = (int64_t)perm_or_null[j0 + k];
+				acc_out[3*o] = o3[3*k]; acc_out[3*o+1] = o3[3*k+1]; acc_out[3*o+2] = o3[3*k+2];
+			}
+		}
+		else
+		{
+			float2 *d2 = reinterpret_cast<float2 *>(acc_out + 3 * j0);
+#pragma unroll
+			for (int m = 0; m < 3 * K / 2; ++m) d2[m] = make_float2(o3[2*m], o3[2*m+1]);
+		}
+	}
+}
+
 constexpr int kTopLevels = 7; // levels 0..7 of the upward / 2..8 of the downward pass run in one CTA
 constexpr int kWideLevel = 1 << 16; // nodes of one rank at a level from which the level gets its own launch
 constexpr int kSubLevels = 7; // deeper levels: chunks of 7 levels, one CTA per subtree (128 nodes at its widest level)
@@ -692,12 +799,33 @@ struct OrderImpl
 		                                                                                   n, L, j_lo, j_hi, eps2, coll);
 		++ctx->launches;
 	}
+	// the pair-list downward pass leaves the leaf level to the L2P kernel when this holds
+	static bool fused_leaf_level(int64_t n, int L)
+	{
+		if (pad4<trl_off(P + 1)>() != 16 || L < 1 || (n & ((1ll << L) - 1)) != 0 || getenv("NBCO_NO_LEAF_FUSION")) return false; // the variable: A/B runs
+		const int64_t C = n >> L;
+		return C == 8 || C == 16 || C == 32;
+	}
+	// nbco_fmm_get_tree: push the leaf level the fused kernel kept in registers (once per evaluation, fmm3.cu keeps the flag)
+	static void finish_leaf_locals(nbco_ctx *ctx, TreeData t, int64_t n, int L, int r, int g)
+	{
+		if (!fused_leaf_level(n, L)) return;
+		if constexpr (pad4<trl_off(P + 1)>() == 16)
+		{
+			const int first = L >= g ? r << (L - g) : r >> (g - L), count = L >= g ? 1 << (L - g) : 1;
+			l2l_level4_kernel<P><<<(4 * count + 127) / 128, 128, 0, ctx->stream>>>(t, L, first, count); ++ctx->launches;
+		}
+	}
 	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
 	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p,
 	                     const CsrView *csr)
 	{
 		if (csr) { downward_by_target(ctx, t, spos, acc_out, perm_or_null, param, fuse_elastic, n, L, r, g, eps2, coll, ev_l2p, *csr); return; }
 		cudaStream_t st = ctx->stream;
+		// uniform leaves and 16-float tuples: the leaf level is pushed inside the L2P kernel (l2lp_uniform_kernel)
+		const bool fused = fused_leaf_level(n, L);
+		const int Lfull = L;
+		if (fused) L = L - 1; // last level of the L2L schedule below
 		// locals of levels 0 and 1 stay zero (nothing is ever admissible there); level l+1 pulls from level l >= 1
 		if (L >= 2)
 		{
@@ -725,10 +853,26 @@ struct OrderImpl
 				++ctx->launches;
 			}
 		}
+		L = Lfull;
 		if (ev_l2p) cudaEventRecord(ev_l2p, st);
 		const int64_t j_lo = seg_start(n, r, g), j_hi = seg_start(n, r + 1, g);
 		const bool uniform = (n & ((1ll << L) - 1)) == 0;
 		const int64_t C = n >> L;
+		if (fused)
+		{
+			if constexpr (pad4<trl_off(P + 1)>() == 16)
+			{
+				const int leaf_lo = (int)(j_lo / C), leaf_hi = (int)(j_hi / C);
+				const int gridf = grid_for(4ll * (leaf_hi - leaf_lo), 128, ctx->sm_count, 16);
+#define NBCO_L2LP_UNIFORM(CC) l2lp_uniform_kernel<P, CC><<<gridf, 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null, param, fuse_elastic, L, leaf_lo, leaf_hi, eps2, coll)
+				if (C == 8) NBCO_L2LP_UNIFORM(8);
+				else if (C == 16) NBCO_L2LP_UNIFORM(16);
+				else NBCO_L2LP_UNIFORM(32);
+#undef NBCO_L2LP_UNIFORM
+			}
+			++ctx->launches;
+			return;
+		}
 		const int grid = grid_for(j_hi - j_lo, 128, ctx->sm_count, 16);
 #define NBCO_L2P_UNIFORM(CC) l2p_uniform_kernel<P, CC><<<grid, 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null, param, fuse_elastic, L, j_lo, j_hi, eps2, coll)
 		if (uniform && C == 8) NBCO_L2P_UNIFORM(8);
@@ -745,6 +889,6 @@ struct OrderImpl
 
 #define NBCO_INSTANTIATE_ORDER(P)                                                                          \
 	extern const OrderOps kOrderOps##P;                                                                    \
-	const OrderOps kOrderOps##P = {OrderImpl<P>::upward, OrderImpl<P>::m2l, OrderImpl<P>::downward, 1};
+	const OrderOps kOrderOps##P = {OrderImpl<P>::upward, OrderImpl<P>::m2l, OrderImpl<P>::downward, 1, OrderImpl<P>::finish_leaf_locals};
 
 } // namespace nbco

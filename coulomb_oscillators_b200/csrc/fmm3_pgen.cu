@@ -378,7 +378,7 @@ struct GenImpl
 
 #define NBCO_GENERIC_ORDER(P) \
 	extern const OrderOps kOrderOps##P; \
-	const OrderOps kOrderOps##P = {GenImpl<P>::upward, GenImpl<P>::m2l, GenImpl<P>::downward, 0};
+	const OrderOps kOrderOps##P = {GenImpl<P>::upward, GenImpl<P>::m2l, GenImpl<P>::downward, 0, nullptr};
 
 #ifndef NBCO_STATIC_ORDER_MAX
 #define NBCO_STATIC_ORDER_MAX 5

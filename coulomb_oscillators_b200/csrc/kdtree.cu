@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(256) exchange_pull_kernel(PeerKd pk, int cur, 
 // =====================================================================================
 //  bottom levels: one CTA per level-lt node, particles resident in shared memory
 // =====================================================================================
-constexpr int kMaxHistBlk = 128;     // histogram mode: blocks of >= 64 slots (at most kBottomCap / 64 of them)
+constexpr int kMaxHistBlk = kBottomCap / 64; // histogram mode: blocks of >= 64 slots
 constexpr u16 kNoSlot = 0xffffu;
 
 struct BlkBox { float lb[3], rb[3]; int chain, axis; }; // box of a block's node, its tie-break chain and split axis
@@ -848,7 +848,7 @@ __device__ __forceinline__ void write_box_keep(const TreeGeom &g, int node, cons
 	}
 }
 
-__global__ void __launch_bounds__(kBottomThreads, 1)
+__global__ void __launch_bounds__(kBottomThreads, kBottomCtasPerSm)
 kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__ spos, int *__restrict__ perm,
                  int64_t n, int lt, int L, int P2, int blk0)
 {

@@ -19,6 +19,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    # NBCO_TEST_POISON=<GiB>: fill that much device memory with a non-zero pattern and give it back to the driver before
+    # the first test, so that buffers the library allocates afterwards do not start out zeroed (a fresh process usually
+    # gets scrubbed pages, which hides reads of memory nobody initialised)
+    gib = int(os.environ.get("NBCO_TEST_POISON", "0") or 0)
+    if gib > 0 and _has_gpu():
+        import torch
+        blocks = [torch.full((1 << 30,), 0xAB, dtype=torch.uint8, device="cuda") for _ in range(gib)]
+        torch.cuda.synchronize()
+        del blocks
+        torch.cuda.empty_cache()
+
+
 def _has_gpu():
     try:
         import torch

@@ -229,6 +229,29 @@ def test_fmm_unsort_mode_and_fused_elastic():
     assert np.abs(a2 - want).max() <= 2e-5 * np.abs(want).max()
 
 
+def test_leaf_level_fused_into_l2p_is_finished_on_demand_exactly_once():
+    """Uniform leaves at orders <= 3: the leaf level of the L2L pass runs inside the L2P kernel and the leaves'
+    tuples are completed only when nbco_fmm_get_tree asks for them (fmm3_order.cuh, l2lp_uniform_kernel)."""
+    n = 1 << 15
+    st = nb.init_ga(n)
+    par = nb.default_param(n)
+    ctx = nb.Context(order=3, unsort=0, m2l_first=1)
+    pos, vel = st[0].copy(), st[1].copy()
+    acc = ctx.eval_host(nb.EVAL_FMM3_KD, pos, vel, par)
+    t1 = ctx.fmm_tree()
+    t2 = ctx.fmm_tree()                       # a second read must not push the level again
+    assert np.array_equal(t1["local"], t2["local"])
+    orc = Oracle(order=3, unsort=0, m2l_first=1)
+    opos, ovel = st[0].copy(), st[1].copy()
+    oacc = orc.fmm3_kd(opos, ovel, par)
+    OT = orc.tree()
+    L = t1["levels"]
+    leaves = slice((1 << L) - 1, (1 << (L + 1)) - 1)
+    assert np.abs(t1["local"][leaves] - OT["local"][leaves]).max() <= 1e-5 * np.abs(OT["local"]).max()
+    m, mx = mean_rel_err(acc, oacc)
+    assert m < TOL_MEAN and mx < TOL_MAX, (m, mx)
+
+
 def test_track_ids_follow_the_particles_through_rebuilds():
     """optional identity array (the reference loses identity at every rebuild, fmm_cart3_kdtree.cuh:1626): after several
     rebuilds ids[j] still names the input particle stored at j -- a run with unsort = 1 (input order kept) is the check"""

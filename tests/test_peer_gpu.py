@@ -35,9 +35,9 @@ def run_ranks(fn, world):
         t.start()
     for t in th:
         t.join()
-    for e in errs:
-        if e is not None:
-            raise e
+    bad = [(r, e) for r, e in enumerate(errs) if e is not None]
+    if bad:  # every rank's error: a barrier time-out on one rank is usually the echo of another rank's failure
+        raise RuntimeError("; ".join(f"rank {r}: {type(e).__name__}: {e}" for r, e in bad)) from bad[0][1]
 
 
 # two ranks only: with more ranks on ONE device the spinning barrier kernels of the waiting ranks and the kernels of
