@@ -619,18 +619,25 @@ __global__ void __launch_bounds__(256) retire_kernel(const TravArgs a, u32 *__re
 	if (gtid == 0) { a.cnt[2] = a.cnt[16]; a.cnt[3] = 0; a.cnt[4] = 0; }
 }
 
-// (3) the lists of the surviving records
+// (3) the lists of the surviving records.  Four consecutive records per thread (one 16-byte load of R): a tile of 1024 records
+// costs one pair of list-counter atomics and two CTA barriers -- with one record per thread the kernel was bound by the
+// latency of those atomics (0.067 ms for 6 M records at N = 2^24, 80 MB of traffic).
 __global__ void __launch_bounds__(256) emit_kernel(const TravArgs a, const int2 *__restrict__ V, const u32 *__restrict__ R)
 {
 	__shared__ u32 wtot[8][2];
 	__shared__ u32 base[2];
 	const u32 count = a.cnt[11];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (u32 i0 = blockIdx.x * blockDim.x; i0 < count; i0 += gridDim.x * blockDim.x)
+	for (u32 i0 = blockIdx.x * (blockDim.x * 4u); i0 < count; i0 += gridDim.x * (blockDim.x * 4u))
 	{
-		const u32 i = i0 + threadIdx.x;
-		const u32 rec = i < count ? R[i] : 0u, k = rec & 7u;
-		const u32 mine = (k == 1u ? 1u : 0u) | (k == 2u ? 1u << 16 : 0u);
+		const u32 i = i0 + 4u * threadIdx.x;
+		u32 rec[4] = {0u, 0u, 0u, 0u};
+		if (i + 3u < count) { const uint4 r4 = *reinterpret_cast<const uint4 *>(R + i); rec[0] = r4.x; rec[1] = r4.y; rec[2] = r4.z; rec[3] = r4.w; }
+		else
+			for (int e = 0; e < 4; ++e) if (i + e < count) rec[e] = R[i + e];
+		u32 mine = 0;
+#pragma unroll
+		for (int e = 0; e < 4; ++e) { const u32 k = rec[e] & 7u; mine += (k == 1u ? 1u : 0u) + (k == 2u ? 1u << 16 : 0u); }
 		u32 incl = mine;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
@@ -650,12 +657,17 @@ __global__ void __launch_bounds__(256) emit_kernel(const TravArgs a, const int2 
 		const u32 excl = incl - mine;
 		u32 s1 = base[0] + (excl & 0xffffu), s2 = base[1] + (excl >> 16);
 		for (int w = 0; w < warp; ++w) { s1 += wtot[w][0]; s2 += wtot[w][1]; }
-		if (k == 1u || k == 2u)
+#pragma unroll
+		for (int e = 0; e < 4; ++e)
 		{
-			const int2 np = V[i];
-			const int2 tagged = make_int2(np.x | (int)(((rec >> 3) & 3u) << kFlagShift), np.y);
-			if (k == 1u && s1 < a.cap_p2p) a.p2p[s1] = tagged;
-			if (k == 2u && s2 < a.cap_m2l) a.m2l[s2] = tagged;
+			const u32 k = rec[e] & 7u;
+			if (k == 1u || k == 2u)
+			{
+				const int2 np = V[i + e];
+				const int2 tagged = make_int2(np.x | (int)(((rec[e] >> 3) & 3u) << kFlagShift), np.y);
+				if (k == 1u) { if (s1 < a.cap_p2p) a.p2p[s1] = tagged; ++s1; }
+				else { if (s2 < a.cap_m2l) a.m2l[s2] = tagged; ++s2; }
+			}
 		}
 		__syncthreads();
 	}

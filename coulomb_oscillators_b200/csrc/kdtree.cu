@@ -1015,7 +1015,8 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 			__syncthreads();
 			// (4) rank the candidates of every block by counting (a group of warps per block)
 			{
-				const int wpb = nblk >= 32 ? 1 : 32 / nblk, ngroups = 32 / wpb;
+				constexpr int kWarps = kBottomThreads / 32;
+				const int wpb = nblk >= kWarps ? 1 : kWarps / nblk, ngroups = kWarps / wpb;
 				const int gl = (warp % wpb) * 32 + lane, gstride = wpb * 32;
 				for (int q = warp / wpb; q < nblk; q += ngroups)
 				{

@@ -3,6 +3,7 @@ host threads, wired with nbco_peer_attach_local instead of CUDA IPC.  Everything
 per-rank subtree build, published centres / multipoles / positions, owner-indexed remote reads in the traversal,
 M2L, P2P and top-level M2M kernels, flag barriers, rebuild-time range exchange.  (tools/peer_check.py runs the
 same comparison with one process per GPU over NVLink.)"""
+import gc
 import threading
 
 import numpy as np
@@ -30,11 +31,21 @@ def run_ranks(fn, world):
         except Exception as e:  # noqa: BLE001
             errs[r] = e
 
-    th = [threading.Thread(target=wrap, args=(r,)) for r in range(world)]
-    for t in th:
-        t.start()
-    for t in th:
-        t.join()
+    # No cyclic garbage collection while the rank threads run: collecting a context left over from an earlier test calls
+    # nbco_destroy -> cudaFree, and every cudaFree waits for the whole device, i.e. for the barrier kernel of the rank that
+    # is waiting for this thread (30 s per freed buffer until the barrier gives up).  An artefact of sharing one device.
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        th = [threading.Thread(target=wrap, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+    finally:
+        if was_enabled:
+            gc.enable()
     bad = [(r, e) for r, e in enumerate(errs) if e is not None]
     if bad:  # every rank's error: a barrier time-out on one rank is usually the echo of another rank's failure
         raise RuntimeError("; ".join(f"rank {r}: {type(e).__name__}: {e}" for r, e in bad)) from bad[0][1]
