@@ -837,7 +837,7 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 template <int G>
 __global__ void __launch_bounds__(256)
 p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap, const float *__restrict__ spos,
-           float *__restrict__ acc, int64_t n, int L, float eps2, PeerTab peers)
+           float *__restrict__ acc, int64_t n, int L, float eps2, PeerTab peers, u32 *__restrict__ nearbits)
 {
 	const int lane = threadIdx.x & (G - 1);
 	const int groups = (gridDim.x * blockDim.x) / G;
@@ -858,6 +858,7 @@ p2p_kernel(const int2 *__restrict__ list, const u32 *__restrict__ count, u32 cap
 			if (!((flags >> dir) & 1)) continue; // another rank owns these targets
 			const int64_t ti = dir ? i2 : i1, si = dir ? i1 : i2;
 			const int tm = dir ? m2 : m1, sm = dir ? m1 : m2;
+			if (nearbits && lane == 0) { const int tl = dir ? l2 : l1; atomicOr(nearbits + (tl >> 5), 1u << (tl & 31)); } // sparse near field: rows of this leaf are live
 			// multi-GPU: the particles of a remote source leaf are read from their owner's published positions
 			const float *__restrict__ src = spos;
 			if (peers.g > 0)
@@ -923,7 +924,8 @@ struct FmmPlan
 	int64_t p2p_n = 0, m2l_n = 0;
 	u32 cap_list = 0, cap_front = 0;
 	KdTree kd;
-	DevBuf center, mpole, local, tmp3, accn;
+	DevBuf center, mpole, local, tmp3, accn, nearbits;
+	bool accn_zero = false; // accn is known to be all zero (the sparse near-field path leaves it that way)
 	DevBuf p2p, m2l, frontA, frontB, cnt, mfac;
 	DevBuf csr_deg, csr_off, csr_src, csr_bsum;   // lists bucketed by target (cfg.reproducible)
 	u32 cap_src = 0;
@@ -986,6 +988,7 @@ static int ensure_plan(nbco_ctx *ctx, int64_t n)
 	NBCO_TRY(p.center.reserve(16 * nt));
 	NBCO_TRY(p.mpole.reserve(4 * nt * p.sM)); NBCO_TRY(p.local.reserve(4 * nt * p.sL));
 	NBCO_TRY(p.tmp3.reserve(12 * (size_t)n)); NBCO_TRY(p.accn.reserve(12 * (size_t)n));
+	p.accn_zero = false;
 	if (p.cap_list < (u32)std::min<int64_t>(8ll * p.ntot + 1024, 0x7fffffff))
 	{
 		p.cap_list = (u32)std::min<int64_t>(8ll * p.ntot + 1024, 0x7fffffff);
@@ -1301,14 +1304,29 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	}
 	else
 	{
-	NBCO_CUDA(cudaMemsetAsync(accn, 0, 12 * (size_t)n, st));
+	// sparse near field (OrderOps::sparse_near): far fewer leaf pairs than leaves at the headline size, so the pair kernel
+	// marks the leaves it adds to and the L2P kernel reads and re-zeroes only their rows: 2^L bits are cleared per evaluation
+	// instead of 12 n bytes, and acc_near is read only where it is not zero
+	u32 *nearbits = nullptr;
+	if (ops.sparse_near && ops.sparse_near(n, L) && !getenv("NBCO_DENSE_NEAR"))
+	{
+		const size_t words = (((size_t)1 << L) + 31) / 32;
+		NBCO_TRY(p.nearbits.reserve(4 * words));
+		nearbits = p.nearbits.as<u32>();
+		NBCO_CUDA(cudaMemsetAsync(nearbits, 0, 4 * words, st));
+		if (!p.accn_zero) NBCO_CUDA(cudaMemsetAsync(accn, 0, 12 * (size_t)n, st));
+	}
+	else
+		NBCO_CUDA(cudaMemsetAsync(accn, 0, 12 * (size_t)n, st));
+	p.accn_zero = false; // until the L2P kernel of this evaluation is enqueued
+	t.nearbits = nearbits;
 	NBCO_CUDA(cudaEventRecord(p.ev[PH_P2P], st)); // the p2p phase is exactly one kernel
 	if (c.coll)
 	{
 		const int blocks = ctx->sm_count * 8;
 #define P2P_LAUNCH(G)                                                                                              \
 		do {                                                                                                       \
-			p2p_kernel<G><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2, t.peers); \
+			p2p_kernel<G><<<blocks, 256, 0, st>>>(a.p2p, a.cnt + 0, a.cap_p2p, spos, accn, n, L, c.eps2, t.peers, nearbits); \
 		} while (0)
 		if (p.mlt_max <= 4) P2P_LAUNCH(4);
 		else if (p.mlt_max <= 8) P2P_LAUNCH(8);
@@ -1325,6 +1343,7 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 	ops.downward(ctx, t, spos, accn, d_acc, c.unsort ? p.kd.perm.as<int>() : nullptr, d_param, fuse_elastic ? 1 : 0, n, L, c.rank, g, c.eps2, c.coll,
 	             p.ev[PH_L2P], nullptr);
 	p.leaf_pending = 1;
+	p.accn_zero = nearbits != nullptr;
 	}
 	if (peer) NBCO_TRY(peer_barrier(ctx)); // nobody reads this rank's centres / multipoles / positions any more
 	eval_check_kernel<<<1, 32, 0, st>>>(a.cnt, p.cap_list); LAUNCHED(ctx);
@@ -1487,7 +1506,7 @@ void fmm3_destroy(nbco_ctx *ctx)
 	if (!ctx->fmm) return;
 	FmmPlan &p = *ctx->fmm;
 	kd_release(p.kd);
-	DevBuf *all[] = {&p.center, &p.mpole, &p.local, &p.tmp3, &p.accn, &p.p2p, &p.m2l, &p.frontA, &p.frontB, &p.cnt, &p.mfac,
+	DevBuf *all[] = {&p.center, &p.mpole, &p.local, &p.tmp3, &p.accn, &p.nearbits, &p.p2p, &p.m2l, &p.frontA, &p.frontB, &p.cnt, &p.mfac,
 	                 &p.csr_deg, &p.csr_off, &p.csr_src, &p.csr_bsum};
 	for (DevBuf *b : all) b->release();
 	if (p.ev_ok)

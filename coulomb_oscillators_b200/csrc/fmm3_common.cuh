@@ -118,6 +118,9 @@ struct TreeData
 	float *local;     // sL floats per node, traceless tuple orders 0..P
 	int sM, sL;
 	PeerTab peers;
+	// sparse near field (pair-list flow, OrderOps::sparse_near): bit (leaf) is set when the pair kernel added something to
+	// the rows of that leaf in acc_near; the L2P kernel reads (and re-zeroes) only those rows.  nullptr: acc_near is dense
+	const u32 *nearbits = nullptr;
 };
 
 // centre / multipole tuple of a node that may live on another GPU
@@ -215,7 +218,7 @@ struct OrderOps
 	// csr == nullptr: pair lists (M2L done by m2l(), near field summed into acc_near by the pair kernel); csr != nullptr:
 	// by-target flow: the levels gather their M2L sources themselves (no m2l() call, locals need no zero-fill) and the
 	// L2P kernel gathers the near field (acc_near unused)
-	void (*downward)(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
+	void (*downward)(nbco_ctx *ctx, TreeData t, const float *spos, float *acc_near, float *acc_out,
 	                 const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g,
 	                 float eps2, int coll, cudaEvent_t ev_l2p /* recorded between the L2L levels and the L2P kernel */,
 	                 const CsrView *csr);
@@ -223,6 +226,9 @@ struct OrderOps
 	// pair-list flow: downward() may leave the leaf level of the L2L pass to its L2P kernel (locals of the leaves then hold
 	// the M2L sums only); this pushes that level for callers that read the tuples back.  nullptr: never fused
 	void (*finish_leaf_locals)(nbco_ctx *ctx, TreeData t, int64_t n, int L, int r, int g);
+	// 1: for this (n, L) downward() reads acc_near only where t.nearbits says so and leaves acc_near all zero again, so the
+	// caller clears the bit map (2^L bits) instead of acc_near (12 n bytes) before the pair kernel.  nullptr: never
+	int (*sparse_near)(int64_t n, int L);
 };
 const OrderOps *order_ops(int order);
 

@@ -620,9 +620,11 @@ l2p_uniform_kernel(TreeData t, const float *__restrict__ spos, const float *__re
 // tuple is never written: against the two-kernel form this saves one 64-byte write and one 64-byte read per leaf and
 // three of every four expansions of the same tuple (nbco_fmm_get_tree finishes the leaf level on demand,
 // finish_leaf_locals below).  Same operations in the same order as l2l_level4_kernel + l2p_uniform_kernel: bit-identical.
+// Sparse near field: with t.nearbits the rows of acc_near are read only for the leaves the pair kernel marked, and those
+// rows are zeroed again behind the output stores, so the caller never clears acc_near (OrderOps::sparse_near).
 template <int P, int C>
 __global__ void __launch_bounds__(128)
-l2lp_uniform_kernel(TreeData t, const float *__restrict__ spos, const float *__restrict__ acc_near, float *__restrict__ acc_out,
+l2lp_uniform_kernel(TreeData t, const float *__restrict__ spos, float *__restrict__ acc_near, float *__restrict__ acc_out,
                     const int *__restrict__ perm_or_null, const float *__restrict__ param, int fuse_elastic, int L, int leaf_lo, int leaf_hi, float eps2, int coll)
 {
 	static_assert(pad4<trl_off(P + 1)>() == 16 && C % 4 == 0, "four float4 per tuple, C / 4 particles per lane");
@@ -644,9 +646,21 @@ l2lp_uniform_kernel(TreeData t, const float *__restrict__ spos, const float *__r
 		const int64_t j0 = (int64_t)leaf * C + sub * K;
 		float tp[3 * K], an[3 * K];
 		{
-			const float2 *p2 = reinterpret_cast<const float2 *>(spos + 3 * j0), *a2 = reinterpret_cast<const float2 *>(acc_near + 3 * j0);
+			const float2 *p2 = reinterpret_cast<const float2 *>(spos + 3 * j0);
 #pragma unroll
-			for (int m = 0; m < 3 * K / 2; ++m) { const float2 v = p2[m], w = a2[m]; tp[2*m] = v.x; tp[2*m+1] = v.y; an[2*m] = w.x; an[2*m+1] = w.y; }
+			for (int m = 0; m < 3 * K / 2; ++m) { const float2 v = p2[m]; tp[2*m] = v.x; tp[2*m+1] = v.y; }
+		}
+		// sparse near field: the rows of a leaf that no pair touched are zero and are neither read nor written; the rows that
+		// were touched are read here and zeroed again at the END of the iteration (a store issued right behind a load of the
+		// same address stalls the load/store unit until the data is back: 0.22 -> 0.62 ms, profiles/r02_notes.md)
+		const bool touched = !t.nearbits || ((t.nearbits[leaf >> 5] >> (leaf & 31)) & 1u);
+#pragma unroll
+		for (int m = 0; m < 3 * K; ++m) an[m] = 0.f;
+		if (touched)
+		{
+			const float2 *a2 = reinterpret_cast<const float2 *>(acc_near + 3 * j0);
+#pragma unroll
+			for (int m = 0; m < 3 * K / 2; ++m) { const float2 w = a2[m]; an[2*m] = w.x; an[2*m+1] = w.y; }
 		}
 		float Lp[16], Lc[16], S[sym_off(P + 1)];
 #pragma unroll
@@ -718,6 +732,12 @@ l2lp_uniform_kernel(TreeData t, const float *__restrict__ spos, const float *__r
 #pragma unroll
 			for (int m = 0; m < 3 * K / 2; ++m) d2[m] = make_float2(o3[2*m], o3[2*m+1]);
 		}
+		if (touched && t.nearbits)
+		{
+			float2 *a2 = reinterpret_cast<float2 *>(acc_near + 3 * j0);
+#pragma unroll
+			for (int m = 0; m < 3 * K / 2; ++m) a2[m] = make_float2(0.f, 0.f);
+		}
 	}
 }
 
@@ -763,7 +783,7 @@ struct OrderImpl
 	}
 	static void m2l(nbco_ctx *ctx, TreeData t, const int2 *list, const unsigned *count, unsigned cap, float eps2)
 	{
-		m2l_kernel<P><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2); ++ctx->launches;
+		m2l_kernel<P><<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2); ++ctx->launches; // 12 .. 24 CTAs per SM: same time (bound by the reductions in L2, profiles/r02_notes.md)
 	}
 	// by-target flow: same level schedule as below (top levels in one CTA, chunks of kSubLevels levels per subtree CTA
 	// while a level is small, one launch per wide level), every node gathers its own M2L row
@@ -806,6 +826,7 @@ struct OrderImpl
 		const int64_t C = n >> L;
 		return C == 8 || C == 16 || C == 32;
 	}
+	static int sparse_near(int64_t n, int L) { return fused_leaf_level(n, L) ? 1 : 0; } // l2lp_uniform_kernel honours t.nearbits
 	// nbco_fmm_get_tree: push the leaf level the fused kernel kept in registers (once per evaluation, fmm3.cu keeps the flag)
 	static void finish_leaf_locals(nbco_ctx *ctx, TreeData t, int64_t n, int L, int r, int g)
 	{
@@ -816,7 +837,7 @@ struct OrderImpl
 			l2l_level4_kernel<P><<<(4 * count + 127) / 128, 128, 0, ctx->stream>>>(t, L, first, count); ++ctx->launches;
 		}
 	}
-	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
+	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, float *acc_near, float *acc_out,
 	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p,
 	                     const CsrView *csr)
 	{
@@ -889,6 +910,6 @@ struct OrderImpl
 
 #define NBCO_INSTANTIATE_ORDER(P)                                                                          \
 	extern const OrderOps kOrderOps##P;                                                                    \
-	const OrderOps kOrderOps##P = {OrderImpl<P>::upward, OrderImpl<P>::m2l, OrderImpl<P>::downward, 1, OrderImpl<P>::finish_leaf_locals};
+	const OrderOps kOrderOps##P = {OrderImpl<P>::upward, OrderImpl<P>::m2l, OrderImpl<P>::downward, 1, OrderImpl<P>::finish_leaf_locals, OrderImpl<P>::sparse_near};
 
 } // namespace nbco

@@ -352,7 +352,7 @@ struct GenImpl
 	{
 		g_m2l_kernel<<<ctx->sm_count * 8, 128, 0, ctx->stream>>>(t, list, count, cap, eps2, P); ++ctx->launches;
 	}
-	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, const float *acc_near, float *acc_out,
+	static void downward(nbco_ctx *ctx, TreeData t, const float *spos, float *acc_near, float *acc_out,
 	                     const int *perm_or_null, const float *param, int fuse_elastic, int64_t n, int L, int r, int g, float eps2, int coll, cudaEvent_t ev_l2p,
 	                     const CsrView *)
 	{
@@ -378,7 +378,7 @@ struct GenImpl
 
 #define NBCO_GENERIC_ORDER(P) \
 	extern const OrderOps kOrderOps##P; \
-	const OrderOps kOrderOps##P = {GenImpl<P>::upward, GenImpl<P>::m2l, GenImpl<P>::downward, 0, nullptr};
+	const OrderOps kOrderOps##P = {GenImpl<P>::upward, GenImpl<P>::m2l, GenImpl<P>::downward, 0, nullptr, nullptr};
 
 #ifndef NBCO_STATIC_ORDER_MAX
 #define NBCO_STATIC_ORDER_MAX 5
