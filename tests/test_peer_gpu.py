@@ -20,6 +20,9 @@ def plain_traversal_launches(monkeypatch):
     # several ranks share ONE device here: a cooperative traversal grid does not overlap with the other ranks'
     # barrier kernels (they would wait for each other until the barrier times out), so use one launch per round
     monkeypatch.setenv("NBCO_TRAVERSE", "launches")
+    # threads of one process arrive within milliseconds of each other: a short bound keeps a failure cheap (the library
+    # reads the variable once, at the first barrier of the process)
+    monkeypatch.setenv("NBCO_PEER_TIMEOUT_S", "10")
 
 
 def run_ranks(fn, world):
