@@ -77,9 +77,18 @@ struct TreeGeom
 	float *size2;            // kd_size per node
 	int *splitdim;           // widest axis per node
 	int *chain;              // tie-break chain per node
+	// Axis and chain the BUILD splits a node by.  Ordinary trees: the same arrays as splitdim / chain.  Shallow trees (a
+	// level-(L-1) node holds more particles than a bottom CTA): the build runs deeper than the tree, and the nodes from the
+	// leaf level on ("virtual" below it) split by the axis and chain of their parent, so that the concatenation of the
+	// virtual leaves is the leaf sorted along its parent's axis -- what the reference's per-level sort leaves behind.
+	int *baxis, *bchain;
+	int first_leaf;          // kd_beg(L) of the TREE: nodes from here on inherit when baxis != splitdim
 };
 
-__device__ __forceinline__ void write_box(const TreeGeom &g, int node, const float *lb, const float *rb, int parent_chain)
+// inherit: this node splits like its parent (see TreeGeom::baxis)
+__device__ __forceinline__ bool kd_inherits(const TreeGeom &g, int node) { return g.baxis != g.splitdim && node >= g.first_leaf && node > 0; }
+
+__device__ __forceinline__ void write_box(const TreeGeom &g, int node, const float *lb, const float *rb, int parent_chain, int parent_axis)
 {
 	g.lbound[3*node] = lb[0]; g.lbound[3*node+1] = lb[1]; g.lbound[3*node+2] = lb[2];
 	g.rbound[3*node] = rb[0]; g.rbound[3*node+1] = rb[1]; g.rbound[3*node+2] = rb[2];
@@ -87,6 +96,12 @@ __device__ __forceinline__ void write_box(const TreeGeom &g, int node, const flo
 	g.splitdim[node] = ax;
 	g.chain[node] = chain_push(ax, parent_chain);
 	g.size2[node] = box_size2(lb, rb);
+	if (g.baxis != g.splitdim)
+	{
+		const bool inh = kd_inherits(g, node);
+		g.baxis[node] = inh ? parent_axis : ax;
+		g.bchain[node] = inh ? parent_chain : chain_push(ax, parent_chain);
+	}
 }
 
 
@@ -135,7 +150,9 @@ struct KdTree
 {
 	int64_t n = 0;
 	int L = 0, lt = 0;
-	DevBuf lbound, rbound, size2, splitdim, chain;   // per node
+	int Lb = 0;          // depth the BUILD runs to: L, or deeper for shallow trees (virtual levels, TreeGeom::baxis)
+	DevBuf lbound, rbound, size2, splitdim, chain;   // per node (of the build: 2^(Lb+1) - 1; the tree's nodes are a prefix)
+	DevBuf baxis, bchain; // only when Lb > L
 	DevBuf payA, payB;   // (x, y, z, id) records, ping-pong between the top levels (16 B / particle each)
 	DevBuf hist, seg;    // per-segment linear histograms and selection state of the current top level
 	DevBuf spos, perm, bbox;

@@ -92,7 +92,7 @@ __global__ void root_box_kernel(TreeGeom g, const u32 *__restrict__ bb)
 	{
 		float lb[3], rb[3];
 		for (int k = 0; k < 3; ++k) { lb[k] = unordered_bits(bb[k]); rb[k] = unordered_bits(bb[3+k]); }
-		write_box(g, 0, lb, rb, kNoAxis | (kNoAxis << 2) | (kNoAxis << 4));
+		write_box(g, 0, lb, rb, kNoAxis | (kNoAxis << 2) | (kNoAxis << 4), kNoAxis);
 	}
 }
 
@@ -125,7 +125,7 @@ top_hist_kernel(const float4 *__restrict__ pay, TreeGeom g, u32 *__restrict__ hi
 	for (int b = threadIdx.x; b < kBins; b += kTopThreads) sh[b] = 0;
 	__syncthreads();
 	const TileRange r = tile_range(n, l, tps, tile, seg0, lb, base);
-	const int node = kd_beg(l) + r.seg, axis = g.splitdim[node];
+	const int node = kd_beg(l) + r.seg, axis = g.baxis[node];
 	const float lo = g.lbound[3*node + axis], scale = bin_scale(lo, g.rbound[3*node + axis], kBins);
 	int64_t j = r.a + threadIdx.x;
 	for (; j + 3 * kTopThreads < r.b; j += 4 * kTopThreads)
@@ -203,7 +203,7 @@ top_partition_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, Tr
 	const u32 lt_mask = (1u << lane) - 1u;
 	SegState *sp = st + (r.seg - seg0);
 	const u32 pb = sp->pb, less = sp->less, eq = sp->eq;
-	const int node = kd_beg(l) + r.seg, axis = g.splitdim[node];
+	const int node = kd_beg(l) + r.seg, axis = g.baxis[node];
 	const float lo = g.lbound[3*node + axis], scale = bin_scale(lo, g.rbound[3*node + axis], kBins);
 	u32 rmin = 0xffffffffu;
 	for (int64_t c0 = r.a; c0 < r.b; c0 += kChunk)
@@ -309,7 +309,7 @@ top_resolve_kernel(float4 *__restrict__ out, float4 *__restrict__ scratch, TreeG
 	__shared__ u32 s_minr;
 	const int seg = seg0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	const SegState s = st[blockIdx.x];
-	const int node = kd_beg(l) + seg, axis = g.splitdim[node], chain = g.chain[node];
+	const int node = kd_beg(l) + seg, axis = g.baxis[node], chain = g.bchain[node];
 	const int64_t s0 = seg_start(n, seg, l);
 	const u32 kleft = (u32)(seg_start(n, 2 * (int64_t)seg + 1, l + 1) - seg_start(n, 2 * (int64_t)seg, l + 1));
 	const u32 eq = s.eq, need = kleft - s.less; // 1 <= need <= eq
@@ -397,10 +397,10 @@ top_resolve_kernel(float4 *__restrict__ out, float4 *__restrict__ scratch, TreeG
 		const int pch = chain;
 		const float save = rb[axis];
 		rb[axis] = unordered_bits(piv[0]);
-		write_box(g, 2*node + 1, lb, rb, pch);
+		write_box(g, 2*node + 1, lb, rb, pch, axis);
 		rb[axis] = save;
 		lb[axis] = unordered_bits(min(s_minr, s.rmin));
-		write_box(g, 2*node + 2, lb, rb, pch);
+		write_box(g, 2*node + 2, lb, rb, pch, axis);
 	}
 }
 
@@ -489,7 +489,7 @@ __global__ void root_box_peer_kernel(TreeGeom g, PeerKd pk)
 		}
 		float lb[3], rb[3];
 		for (int k = 0; k < 3; ++k) { lb[k] = unordered_bits(mn[k]); rb[k] = unordered_bits(mx[k]); }
-		write_box(g, 0, lb, rb, kNoAxis | (kNoAxis << 2) | (kNoAxis << 4));
+		write_box(g, 0, lb, rb, kNoAxis | (kNoAxis << 2) | (kNoAxis << 4), kNoAxis);
 		int64_t *r0 = scr_range(pk.scr[pk.me], 0);
 		r0[0] = 0; r0[1] = pk.lo[pk.me + 1] - pk.lo[pk.me];
 		u32 *dw = kd_dbg(pk.scr[pk.me]);
@@ -587,7 +587,7 @@ top_select_peer_kernel(PeerKd pk, TreeGeom g, int cur /* buffer that holds the p
 	__shared__ CandUnion cu;
 	const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	unsigned char *myscr = pk.scr[pk.me];
-	const int node = kd_beg(l) + seg, axis = g.splitdim[node], chain = g.chain[node];
+	const int node = kd_beg(l) + seg, axis = g.baxis[node], chain = g.bchain[node];
 	const u32 kleft = (u32)(seg_start(n, 2 * (int64_t)seg + 1, l + 1) - seg_start(n, 2 * (int64_t)seg, l + 1));
 	if (tid == 0)
 	{
@@ -686,7 +686,7 @@ top_split_peer_kernel(PeerKd pk, TreeGeom g, int cur, int64_t n, int l)
 	__shared__ u32 run[2];
 	const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	unsigned char *myscr = pk.scr[pk.me];
-	const int node = kd_beg(l) + seg, axis = g.splitdim[node], chain = g.chain[node];
+	const int node = kd_beg(l) + seg, axis = g.baxis[node], chain = g.bchain[node];
 	const u32 *pv = scr_pivot(myscr, l) + 8 * seg;
 	const u32 piv[4] = {pv[0], pv[1], pv[2], pv[3]};
 	const int depth = (int)pv[4];
@@ -755,10 +755,10 @@ top_split_peer_kernel(PeerKd pk, TreeGeom g, int cur, int64_t n, int l)
 		for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
 		const float save = rb[axis];
 		rb[axis] = unordered_bits(piv[0]);
-		write_box(g, 2*node + 1, lb, rb, chain);
+		write_box(g, 2*node + 1, lb, rb, chain, axis);
 		rb[axis] = save;
 		lb[axis] = unordered_bits(minr_all);
-		write_box(g, 2*node + 2, lb, rb, chain);
+		write_box(g, 2*node + 2, lb, rb, chain, axis);
 		// local ranges of the children
 		u32 *dw = kd_dbg(myscr);
 		dw[20 + 4 * l] = mine.less; dw[21 + 4 * l] = ne; dw[22 + 4 * l] = nleft; dw[23 + 4 * l] = (u32)(lbm[seg + 1] - lbm[seg]);
@@ -837,14 +837,15 @@ __device__ __forceinline__ bool slot_tie_less(const BottomSmem &s, u32 sa, u32 s
 }
 
 // write_box (fmm3_common.cuh) that also returns the node's state for the next level
-__device__ __forceinline__ void write_box_keep(const TreeGeom &g, int node, const float *lb, const float *rb, int parent_chain, BlkBox *keep)
+__device__ __forceinline__ void write_box_keep(const TreeGeom &g, int node, const float *lb, const float *rb, int parent_chain, int parent_axis, BlkBox *keep)
 {
-	write_box(g, node, lb, rb, parent_chain);
+	write_box(g, node, lb, rb, parent_chain, parent_axis);
 	if (keep)
 	{
 		const int ax = widest_axis(rb[0] - lb[0], rb[1] - lb[1], rb[2] - lb[2]);
+		const bool inh = kd_inherits(g, node);
 		for (int k = 0; k < 3; ++k) { keep->lb[k] = lb[k]; keep->rb[k] = rb[k]; }
-		keep->axis = ax; keep->chain = chain_push(ax, parent_chain);
+		keep->axis = inh ? parent_axis : ax; keep->chain = inh ? parent_chain : chain_push(ax, parent_chain);
 	}
 }
 
@@ -896,7 +897,7 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 		const int node = kd_beg(lt) + b;
 		BlkBox bx;
 		for (int k = 0; k < 3; ++k) { bx.lb[k] = g.lbound[3*node+k]; bx.rb[k] = g.rbound[3*node+k]; }
-		bx.axis = g.splitdim[node]; bx.chain = g.chain[node];
+		bx.axis = g.baxis[node]; bx.chain = g.bchain[node];
 		s.box[0][0] = bx;
 	}
 	__syncthreads();
@@ -1051,10 +1052,10 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 				for (int k = 0; k < 3; ++k) { lb[k] = bx[tid].lb[k]; rb[k] = bx[tid].rb[k]; }
 				const float save = rb[axis];
 				rb[axis] = unordered_bits(s.b_cutL[tid]);
-				write_box_keep(g, 2*node + 1, lb, rb, pch, bnext ? bnext + 2 * tid : nullptr);
+				write_box_keep(g, 2*node + 1, lb, rb, pch, axis, bnext ? bnext + 2 * tid : nullptr);
 				rb[axis] = save;
 				lb[axis] = unordered_bits(min(s.b_cutR[tid], s.b_rmin[tid]));
-				write_box_keep(g, 2*node + 2, lb, rb, pch, bnext ? bnext + 2 * tid + 1 : nullptr);
+				write_box_keep(g, 2*node + 2, lb, rb, pch, axis, bnext ? bnext + 2 * tid + 1 : nullptr);
 			}
 			cb ^= 1;
 		}
@@ -1065,7 +1066,7 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 			for (int p = tid; p < P2; p += kBottomThreads)
 			{
 				const u32 slot = oin[p];
-				s.ckey[p] = slot != kNoSlot ? ordered_bits(s.c[g.splitdim[node0 + (p >> logB)] * kBottomCap + slot]) : 0xffffffffu;
+				s.ckey[p] = slot != kNoSlot ? ordered_bits(s.c[g.baxis[node0 + (p >> logB)] * kBottomCap + slot]) : 0xffffffffu;
 			}
 			__syncthreads();
 			// (b) rank by counting smaller keys of the block; equal keys (rare) take the slow path
@@ -1090,7 +1091,7 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 					for (int f = 0; f < B; ++f) { const u32 kf = s.ckey[qB + f]; rank += kf < kc ? 1u : 0u; ties += kf == kc ? 1u : 0u; }
 				if (ties > 1u)
 				{
-					const int chain = g.chain[node0 + q];
+					const int chain = g.bchain[node0 + q];
 					for (int f = 0; f < B; ++f)
 					{
 						const u32 sf = oin[qB + f];
@@ -1113,16 +1114,16 @@ kd_bottom_kernel(TreeGeom g, const float4 *__restrict__ pay, float *__restrict__
 				const int64_t i = i0 + q;
 				const int node = node0 + q, qB = q << logB;
 				const int kl = (int)(seg_start(n, 2*i + 1, l + 1) - seg_start(n, 2*i, l + 1));
-				const int axis = g.splitdim[node], pch = g.chain[node];
+				const int axis = g.baxis[node], pch = g.bchain[node];
 				float lb[3], rb[3];
 				for (int k = 0; k < 3; ++k) { lb[k] = g.lbound[3*node+k]; rb[k] = g.rbound[3*node+k]; }
 				const float cl = s.c[axis * kBottomCap + oout[qB + kl - 1]];
 				const float cr = s.c[axis * kBottomCap + oout[last ? qB + kl : qB + (B >> 1)]];
 				const float save = rb[axis];
 				rb[axis] = cl;
-				write_box(g, 2*node + 1, lb, rb, pch);
+				write_box(g, 2*node + 1, lb, rb, pch, axis);
 				rb[axis] = save; lb[axis] = cr;
-				write_box(g, 2*node + 2, lb, rb, pch);
+				write_box(g, 2*node + 2, lb, rb, pch, axis);
 			}
 		}
 		__syncthreads();
@@ -1155,17 +1156,16 @@ int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L)
 	t.n = n; t.L = L;
 	int lt = 0;
 	while (((n - 1) >> lt) + 1 > kBottomCap) ++lt; // first level whose segments fit a bottom CTA
-	// the last sorting level must run in the bottom kernel (the top levels only partition)
-	t.lt = std::min(lt, L - 1);
-	if (((n - 1) >> t.lt) + 1 > kBottomCap)
-	{
-		set_error("max_level %d leaves %lld particles per level-%d node; at most %d are supported", L,
-		          (long long)(((n - 1) >> t.lt) + 1), t.lt, kBottomCap);
-		return NBCO_ERR_INVALID;
-	}
-	const size_t nt = ((size_t)1 << (L + 1)) - 1;
+	// The last sorting level must run in the bottom kernel (the top levels only partition).  Ordinary trees: lt <= L - 1.
+	// Shallow trees (fmm_cart3_kdtree.cuh:1508-1512 accepts any max_level): the build continues below the leaves with
+	// virtual levels that split along the parent's axis (TreeGeom::baxis) until a segment fits a bottom CTA.
+	t.Lb = std::max(L, lt + 1);
+	t.lt = std::min(lt, t.Lb - 1);
+	if (t.Lb > 30) { set_error("kd build: depth %d", t.Lb); return NBCO_ERR_INVALID; }
+	const size_t nt = ((size_t)1 << (t.Lb + 1)) - 1;
 	NBCO_TRY(t.lbound.reserve(12 * nt)); NBCO_TRY(t.rbound.reserve(12 * nt)); NBCO_TRY(t.size2.reserve(4 * nt));
 	NBCO_TRY(t.splitdim.reserve(4 * nt)); NBCO_TRY(t.chain.reserve(4 * nt));
+	if (t.Lb > L) { NBCO_TRY(t.baxis.reserve(4 * nt)); NBCO_TRY(t.bchain.reserve(4 * nt)); }
 	NBCO_TRY(t.payA.reserve(16 * (size_t)n));
 	if (t.lt > 0) NBCO_TRY(t.payB.reserve(16 * (size_t)n));
 	NBCO_TRY(t.spos.reserve(12 * (size_t)n)); NBCO_TRY(t.perm.reserve(4 * (size_t)n));
@@ -1176,9 +1176,16 @@ int kd_reserve(nbco_ctx *ctx, KdTree &t, int64_t n, int L)
 	return NBCO_OK;
 }
 
+static TreeGeom geom_of(KdTree &t)
+{
+	const bool deep = t.Lb > t.L;
+	return TreeGeom{t.lbound.as<float>(), t.rbound.as<float>(), t.size2.as<float>(), t.splitdim.as<int>(), t.chain.as<int>(),
+	                deep ? t.baxis.as<int>() : t.splitdim.as<int>(), deep ? t.bchain.as<int>() : t.chain.as<int>(), kd_beg(t.L)};
+}
+
 void kd_release(KdTree &t)
 {
-	DevBuf *all[] = {&t.lbound, &t.rbound, &t.size2, &t.splitdim, &t.chain, &t.payA, &t.payB, &t.hist, &t.seg, &t.spos, &t.perm, &t.bbox};
+	DevBuf *all[] = {&t.lbound, &t.rbound, &t.size2, &t.splitdim, &t.chain, &t.baxis, &t.bchain, &t.payA, &t.payB, &t.hist, &t.seg, &t.spos, &t.perm, &t.bbox};
 	for (DevBuf *b : all) b->release();
 }
 
@@ -1210,7 +1217,7 @@ static int kd_local_levels(nbco_ctx *ctx, KdTree &t, float4 *pay[2], int cur, in
 {
 	cudaStream_t st = ctx->stream;
 	const int64_t n = t.n;
-	TreeGeom tg{t.lbound.as<float>(), t.rbound.as<float>(), t.size2.as<float>(), t.splitdim.as<int>(), t.chain.as<int>()};
+	TreeGeom tg = geom_of(t);
 	u32 *hist = t.hist.as<u32>();
 	SegState *seg = t.seg.as<SegState>();
 	const int ltop = t.lt; // levels [0, ltop) are partitioned globally
@@ -1239,11 +1246,11 @@ static int kd_local_levels(nbco_ctx *ctx, KdTree &t, float4 *pay[2], int cur, in
 	}
 	int64_t maxseg = ((n - 1) >> ltop) + 1;
 	int P2 = 2; while (P2 < maxseg) P2 <<= 1;
-	while ((P2 >> (t.L - 1 - ltop)) < 2) P2 <<= 1; // the last level sorts blocks of at least 2 slots
+	while ((P2 >> (t.Lb - 1 - ltop)) < 2) P2 <<= 1; // the last level sorts blocks of at least 2 slots
 	if (P2 > kBottomCap) { set_error("internal: bottom block %d", P2); return NBCO_ERR_INVALID; }
 	if (g > ltop) { set_error("more ranks than shared-memory kd blocks (2^%d > 2^%d)", g, ltop); return NBCO_ERR_INVALID; }
 	kd_bottom_kernel<<<1 << (ltop - g), kBottomThreads, kBottomSmemBytes, st>>>(tg, pay[cur], t.spos.as<float>(), t.perm.as<int>(),
-	                                                                            n, ltop, t.L, P2, r << (ltop - g));
+	                                                                            n, ltop, t.Lb, P2, r << (ltop - g));
 	++ctx->launches;
 	NBCO_CUDA(cudaGetLastError());
 	return NBCO_OK;
@@ -1253,7 +1260,7 @@ int kd_build(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bottom, 
 {
 	cudaStream_t st = ctx->stream;
 	const int64_t n = t.n;
-	TreeGeom tg{t.lbound.as<float>(), t.rbound.as<float>(), t.size2.as<float>(), t.splitdim.as<int>(), t.chain.as<int>()};
+	TreeGeom tg = geom_of(t);
 	u32 *bb = t.bbox.as<u32>();
 	static const u32 bb_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
 	NBCO_CUDA(cudaMemcpyAsync(bb, bb_init, sizeof(bb_init), cudaMemcpyHostToDevice, st));
@@ -1276,7 +1283,8 @@ int kd_build_peer(nbco_ctx *ctx, KdTree &t, const float *pos, cudaEvent_t ev_bot
 	static const bool dbg = getenv("NBCO_DEBUG_KD_SYNC") != nullptr; // synchronise and report after every stage
 #define KD_STAGE(name) do { if (dbg) { cudaError_t e_ = cudaStreamSynchronize(st); fprintf(stderr, "[kd_peer rank %d] %-28s %s\n", r, name, cudaGetErrorString(e_)); } } while (0)
 	if (g < 1 || g > 3 || g > t.lt) { set_error("kd_build_peer: %d ranks for %d global levels", world, t.lt); return NBCO_ERR_INVALID; }
-	TreeGeom tg{t.lbound.as<float>(), t.rbound.as<float>(), t.size2.as<float>(), t.splitdim.as<int>(), t.chain.as<int>()};
+	if (t.Lb > t.L) { set_error("kd_build_peer: max_level %d leaves more than %d particles per leaf pair; shallow trees are built on one GPU only", t.L, kBottomCap); return NBCO_ERR_INVALID; }
+	TreeGeom tg = geom_of(t);
 	PeerKd pk;
 	pk.world = world; pk.me = r; pk.g = g;
 	for (int q = 0; q < kMaxPeers; ++q)

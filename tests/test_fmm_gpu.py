@@ -210,6 +210,24 @@ def test_fmm_equal_keys_follow_the_stable_sort_rule():
     check_against_oracle(pos, vel, nb.default_param(n), 2, 0, tol_max=5e-5)
 
 
+@pytest.mark.parametrize("n,max_level,order", [(36000, 2, 3), (20000, 2, 1)])
+def test_shallow_trees_build_with_virtual_levels(n, max_level, order):
+    """max_level so small that a level-(L-1) node holds more particles than a bottom CTA of the kd build (8192): the
+    reference accepts any max_level (fmm_cart3_kdtree.cuh:1508-1512); the build continues below the leaves with virtual
+    levels along the parent's axis (kdtree.cu: kd_reserve, TreeGeom::baxis).  Same gates as every other case."""
+    assert ((n - 1) >> (max_level - 1)) + 1 > 8192
+    st = nb.init_ga(n)
+    check_against_oracle(st[0], st[1], nb.default_param(n), order, 1, max_level=max_level)
+
+
+def test_shallow_tree_with_equal_keys():
+    n = 24000
+    rng = np.random.default_rng(11)
+    pos = (np.round(rng.normal(size=(n, 3)) * 40) / 4000).astype(np.float32)   # ~500 distinct values per axis: many ties
+    vel = rng.normal(size=(n, 3)).astype(np.float32)
+    check_against_oracle(pos, vel, nb.default_param(n), 2, 1, tol_max=5e-5, max_level=2)
+
+
 def test_fmm_unsort_mode_and_fused_elastic():
     n = 40000
     st = nb.init_ga(n)
