@@ -25,6 +25,10 @@
 //     shared memory and a u16 slot permutation that is partitioned level by level (same histogram
 //     selection; blocks of <= 32 slots and the last level are ranked by counting).
 //   * particle data moves once, at the end (sorted positions + permutation).
+//   * shallow trees (max_level so small that a level-(L-1) node exceeds kBottomCap): the order inside a leaf is the
+//     order of its PARENT's sort, so the build simply continues below the leaves with virtual levels that inherit the
+//     parent's axis and tie-break chain (TreeGeom::baxis / bchain) until a segment fits a bottom CTA; the tree's own
+//     arrays are a prefix of the build's.
 
 #include "fmm3_common.cuh"
 

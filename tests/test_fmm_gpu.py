@@ -270,6 +270,30 @@ def test_leaf_level_fused_into_l2p_is_finished_on_demand_exactly_once():
     assert m < TOL_MEAN and mx < TOL_MAX, (m, mx)
 
 
+@pytest.mark.parametrize("n,order", [(1 << 15, 3), (1 << 16, 2)])
+def test_uniform_leaves_unsort_and_options(n, order):
+    """Power-of-two N at orders <= 3 takes the fused leaf kernel with the sparse near field (l2lp_uniform_kernel): the same
+    checks as test_fmm_unsort_mode_and_fused_elastic on that path, plus coll = 0 and repeated evaluations on one context
+    (the kernel must leave acc_near all zero behind)."""
+    st = nb.init_ga(n)
+    par = nb.default_param(n)
+    c0 = nb.Context(order=order, unsort=0)
+    p0, v0 = st[0].copy(), st[1].copy()
+    a0 = c0.eval_host(nb.EVAL_FMM3_KD, p0, v0, par)
+    perm = c0.fmm_tree()["perm"]
+    c1 = nb.Context(order=order, unsort=1)
+    for rep in range(3):                                                      # every evaluation rebuilds and must agree
+        p1, v1 = st[0].copy(), st[1].copy()
+        a1 = c1.eval_host(nb.EVAL_FMM3_KD, p1, v1, par)
+        assert np.array_equal(p1, st[0])
+        m, mx = mean_rel_err(a1[perm], a0)
+        assert mx < 1e-5, (rep, m, mx)
+    a2 = c1.eval_host(nb.EVAL_COULOMB_FMM3_KD, st[0].copy(), st[1].copy(), par)
+    want = a1 - st[0] * par[3:6]
+    assert np.abs(a2 - want).max() <= 2e-5 * np.abs(want).max()
+    check_against_oracle(st[0], st[1], par, order, 1, coll=0)
+
+
 def test_track_ids_follow_the_particles_through_rebuilds():
     """optional identity array (the reference loses identity at every rebuild, fmm_cart3_kdtree.cuh:1626): after several
     rebuilds ids[j] still names the input particle stored at j -- a run with unsort = 1 (input order kept) is the check"""
