@@ -95,11 +95,12 @@ def test_fmm_config2_size_matches_oracle_and_direct():
     assert 0.02 < ours < 0.2   # the reference's own p = 3 accuracy class
 
 
-@pytest.mark.parametrize("name", ["fmm_ga_n3000_p3", "fmm_cube_n4096_p4", "fmm_ga_n2500_p1"])
+@pytest.mark.parametrize("name", ["fmm_ga_n3000_p3", "fmm_cube_n4096_p4", "fmm_ga_n2500_p1", "fmm_ga_n17000_p2_shallow"])
 @pytest.mark.parametrize("m2l_first", [0, 1])
 def test_fmm_matches_reference_fixture(name, m2l_first):
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    ctx = nb.Context(order=int(g["order"]), unsort=0, m2l_first=m2l_first)
+    cfg = {"dens_inhom": float(g["dens_inhom"])} if "dens_inhom" in g.files else {}
+    ctx = nb.Context(order=int(g["order"]), unsort=0, m2l_first=m2l_first, **cfg)
     pos, vel = g["pos"].copy(), g["vel"].copy()
     acc = ctx.eval_host(nb.EVAL_FMM3_KD, pos, vel, g["param"])
     T = ctx.fmm_tree()

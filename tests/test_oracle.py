@@ -10,14 +10,19 @@ import coulomb_oscillators_b200 as nb
 from refs import Oracle, Ref, mean_rel_err, unique_axes
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FIXTURES = ["fmm_ga_n3000_p3", "fmm_cube_n4096_p4", "fmm_ga_n2500_p1"]
+# the last one: a two-level tree whose level-1 nodes hold 8500 particles (shallow: built with virtual levels on the GPU)
+FIXTURES = ["fmm_ga_n3000_p3", "fmm_cube_n4096_p4", "fmm_ga_n2500_p1", "fmm_ga_n17000_p2_shallow"]
+
+
+def fixture_cfg(g):
+    return {"dens_inhom": float(g["dens_inhom"])} if "dens_inhom" in g.files else {}
 
 
 @pytest.mark.parametrize("name", FIXTURES)
 @pytest.mark.parametrize("m2l_first", [0, 1])
 def test_oracle_against_reference_fixture(name, m2l_first):
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    orc = Oracle(order=int(g["order"]), unsort=0, m2l_first=m2l_first)
+    orc = Oracle(order=int(g["order"]), unsort=0, m2l_first=m2l_first, **fixture_cfg(g))
     pos = g["pos"].copy()
     acc = orc.fmm3_kd(pos, None, g["param"])
     T = orc.tree()
