@@ -476,12 +476,14 @@ __device__ __forceinline__ void rec_round(const TravArgs &a, int2 *__restrict__ 
 }
 
 // rounds from the frontier V[cnt[11], cnt[11] + cnt[2]) until nothing is left; cnt[11] = entries of V afterwards
-__global__ void __launch_bounds__(256) traverse_rec_kernel(const TravArgs a, int2 *V, u32 *R, const u32 *seeds, int max_rounds)
+__global__ void __launch_bounds__(256) traverse_rec_kernel(const TravArgs a, int2 *V, u32 *R, const u32 *seeds_arg, int max_rounds)
 {
 	__shared__ u32 wtot[8][3];
 	__shared__ u32 base[3];
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const u32 *seeds = seeds_arg;
 	u32 start = *(volatile u32 *)(a.cnt + 11);
+	if (seeds && *(volatile u32 *)(a.cnt + 20)) seeds = nullptr; // reuse evaluation that fell back to the root
 	grid.sync(); // everybody has read the start before CTA 0 may store the end
 	for (int r = 0; r < max_rounds; ++r)
 	{
@@ -510,19 +512,32 @@ __global__ void traverse_rec_init_kernel(int2 *V, u32 *cnt)
 	if (threadIdx.x == 0 && blockIdx.x == 0)
 	{
 		V[0] = make_int2(0, 0);
-		cnt[0] = 0; cnt[1] = 0; cnt[2] = 1; cnt[3] = 0; cnt[4] = 0; cnt[5] = 0; cnt[11] = 0; cnt[12] = 0;
+		cnt[0] = 0; cnt[1] = 0; cnt[2] = 1; cnt[3] = 0; cnt[4] = 0; cnt[5] = 0; cnt[11] = 0; cnt[12] = 0; cnt[20] = 0;
 	}
 }
 
-__global__ void traverse_reuse_init_kernel(u32 *cnt)
+// Start of a reuse evaluation.  The records only grow between two rebuilds (re-expanded subtrees are appended, retired ones stay
+// as tombstones) and these evaluations are enqueued without a host round trip, so the decision whether the update still fits is
+// taken HERE: while at most `limit` = half of the record capacity is in use, the change list and the retire queue (half the
+// capacity each) cannot overflow and the other half is room for this evaluation's appends; beyond that the evaluation traverses
+// from the root again (cnt[20] = 1: reval / retire / emit return at once, traverse_rec starts from the pair (root, root)), which
+// also compacts the records.  The host guarantees capacity >= 3 x the records of a from-the-root traversal at every rebuild.
+__global__ void traverse_reuse_init_kernel(u32 *cnt, int2 *V, u32 limit)
 {
-	if (threadIdx.x == 0 && blockIdx.x == 0) { cnt[0] = 0; cnt[1] = 0; cnt[5] = 0; cnt[12] = 0; cnt[13] = 0; cnt[14] = 0; cnt[15] = 0; cnt[16] = 0; cnt[17] = 0; cnt[18] = 0; cnt[19] = 0; }
+	if (threadIdx.x == 0 && blockIdx.x == 0)
+	{
+		cnt[0] = 0; cnt[1] = 0; cnt[5] = 0; cnt[12] = 0; cnt[13] = 0; cnt[14] = 0; cnt[15] = 0; cnt[16] = 0; cnt[17] = 0; cnt[18] = 0; cnt[19] = 0;
+		const bool root = cnt[11] > limit;
+		cnt[20] = root ? 1u : 0u;
+		if (root) { V[0] = make_int2(0, 0); cnt[2] = 1; cnt[3] = 0; cnt[4] = 0; cnt[11] = 0; cnt[21] += 1u; /* diagnostics: fallbacks so far */ }
+	}
 }
 
 // (1) which recorded pairs change kind with the new centres?  (kinds 0 and 3 do not depend on the centres)
 __global__ void __launch_bounds__(256) reval_kernel(const TravArgs a, const int2 *__restrict__ V, const u32 *__restrict__ R,
                                                     u32 *__restrict__ clist, u32 cap_c)
 {
+	if (a.cnt[20]) return; // this evaluation traverses from the root (traverse_reuse_init_kernel)
 	const u32 count = a.cnt[11];
 	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
 	{
@@ -562,6 +577,7 @@ __global__ void __launch_bounds__(256) retire_kernel(const TravArgs a, u32 *__re
                                                      u32 *__restrict__ bq, u32 cap_q)
 {
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	if (a.cnt[20]) return; // from-the-root evaluation: nothing to retire (uniform over the grid: no barrier is left waiting)
 	const u32 nc = a.cnt[12];
 	const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
 	const u32 nc_pad = (nc + 31u) & ~31u; // whole warps stay in the loops (warp_reserve shuffles)
@@ -626,6 +642,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const TravArgs a, const int2 
 {
 	__shared__ u32 wtot[8][2];
 	__shared__ u32 base[2];
+	if (a.cnt[20]) return; // from-the-root evaluation: the traversal rounds write the lists themselves
 	const u32 count = a.cnt[11];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	for (u32 i0 = blockIdx.x * (blockDim.x * 4u); i0 < count; i0 += gridDim.x * (blockDim.x * 4u))
@@ -919,6 +936,8 @@ struct FmmPlan
 	int64_t n = 0;
 	int L = 0, ntot = 0, order = 0, offM = 0, offL = 0, sM = 0, sL = 0, mlt_max = 0;
 	int counter = 0, rebuilt = 0, max_level = -1;
+	int64_t rec_n = 0;        // records of the last evaluation's traversal (cnt[11]); rec_fallbacks: reuse evaluations that went back to the root
+	u32 rec_fallbacks = 0;
 	int leaf_pending = 0; // the last downward pass may have kept the leaf level of the L2L pass in registers (OrderOps::finish_leaf_locals)
 	float dens = 0.f;
 	int64_t p2p_n = 0, m2l_n = 0;
@@ -1222,7 +1241,11 @@ static int run_phases(const OrderOps &ops, nbco_ctx *ctx, FmmPlan &p, float *d_p
 		}
 		else
 		{
-			traverse_reuse_init_kernel<<<1, 32, 0, st>>>(a.cnt); LAUNCHED(ctx);
+			// NBCO_REC_LIMIT=<records>: force the from-the-root fallback earlier (tests)
+			const char *lim_s = getenv("NBCO_REC_LIMIT");
+			const long long lim_env = lim_s ? atoll(lim_s) : -1;
+			const u32 limit = lim_env >= 0 ? (u32)std::min<long long>(lim_env, half) : half;
+			traverse_reuse_init_kernel<<<1, 32, 0, st>>>(a.cnt, V, limit); LAUNCHED(ctx);
 			reval_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(a, V, R, clist, half); LAUNCHED(ctx);
 			{
 				u32 *bq = clist + half;
@@ -1377,7 +1400,7 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 	if (sync_all < 0) { const char *e = getenv("NBCO_SYNC_EVERY_EVAL"); sync_all = (e && atoi(e)) ? 1 : 0; }
 	const bool must_sync = rebuild || sync_all || p.ev_npend >= FmmPlan::kEvRing - 1 || getenv("NBCO_DEBUG_TRAV");
 	bool do_build = rebuild;
-	for (int attempt = 0; attempt < 6; ++attempt)
+	for (int attempt = 0; attempt < 12; ++attempt)
 	{
 		p.ev = p.evr[p.ev_head];
 		p.ev_rebuild[p.ev_head] = do_build;
@@ -1396,7 +1419,9 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 			        dbg[12], dbg[16], dbg[13], dbg[14], dbg[15]);
 		}
 		// headroom for the enqueued evaluations that follow: lists at most half full after a rebuild
-		const bool roomy = 2 * p.p2p_n <= (int64_t)p.cap_list && 2 * p.m2l_n <= (int64_t)p.cap_list;
+		// ... and the records of this from-the-root traversal fill at most a third of their array (traverse_reuse_init_kernel)
+		const bool roomy = 2 * p.p2p_n <= (int64_t)p.cap_list && 2 * p.m2l_n <= (int64_t)p.cap_list
+		                   && (!p.rec_valid || 3 * p.rec_n <= (int64_t)p.cap_front);
 		if (!over && (roomy || !rebuild || ctx->peer.active))
 		{
 			++p.counter;
@@ -1411,7 +1436,15 @@ int fmm3_kd_launch(nbco_ctx *ctx, float *d_pos, float *d_acc, int64_t n, const f
 		// a list or a frontier did not fit (or is more than half full): grow and redo this evaluation.  With
 		// unsort == 0 the caller's arrays are already in tree order and the tree is valid: do not build again.
 		if (p.cap_list >= 0x7fffffffu / 2) { if (!over) { ++p.counter; return NBCO_OK; } break; }
-		p.cap_list *= 2; p.cap_front = p.cap_list;
+		{
+			// at least double; jump straight to what the counters of this attempt ask for (they are lower bounds when a
+			// frontier did not fit: the traversal stopped early), so that a strict MAC does not need many repeats
+			int64_t want = 2 * (int64_t)p.cap_list;
+			want = std::max(want, 2 * std::max(p.p2p_n, p.m2l_n) + 1024);
+			if (p.rec_valid) want = std::max(want, 3 * p.rec_n + 1024);
+			p.cap_list = (u32)std::min<int64_t>(want, 0x7fffffff);
+			p.cap_front = p.cap_list;
+		}
 		NBCO_TRY(p.p2p.reserve(8 * (size_t)p.cap_list)); NBCO_TRY(p.m2l.reserve(8 * (size_t)p.cap_list));
 		NBCO_TRY(p.frontA.reserve(8 * (size_t)p.cap_front)); NBCO_TRY(p.frontB.reserve(8 * (size_t)p.cap_front));
 		p.cap_src = (u32)std::min<int64_t>(4ll * p.cap_list, 0x7fffffff);
@@ -1464,7 +1497,7 @@ int fmm3_harvest(nbco_ctx *ctx, int *overflow)
 	}
 	p.ev_npend = 0;
 	p.ev_valid = true;
-	p.p2p_n = h[0]; p.m2l_n = h[1];
+	p.p2p_n = h[0]; p.m2l_n = h[1]; p.rec_n = h[11]; p.rec_fallbacks = h[21];
 	if (perr) { set_error("peer barrier timed out: a rank did not arrive (results since the last synchronisation are invalid)"); return NBCO_ERR_CUDA; }
 	const bool last_over = h[0] > p.cap_list || h[1] > p.cap_list || h[5] != 0;
 	if (h[24])

@@ -342,12 +342,18 @@ def test_fmm_tree_reuse_between_rebuilds():
     assert np.abs(s[1] - o[1]).max() <= 1e-4 * np.abs(o[1]).max()
 
 
-@pytest.mark.parametrize("n,order,m2l_first,dt", [(50000, 3, 1, 5e-4), (200000, 3, 0, 5e-3), (30000, 5, 1, 2e-2)])
-def test_incremental_traversal_gives_the_same_lists(n, order, m2l_first, dt, monkeypatch):
+@pytest.mark.parametrize("n,order,m2l_first,dt,rec_limit", [
+    (50000, 3, 1, 5e-4, None), (200000, 3, 0, 5e-3, None), (30000, 5, 1, 2e-2, None),
+    # the records outgrow their budget (forced through NBCO_REC_LIMIT): the reuse evaluation decides ON THE DEVICE to traverse
+    # from the root again (traverse_reuse_init_kernel): always (0), and only once the appended records pass the limit (20000)
+    (50000, 3, 1, 5e-3, 0), (30000, 3, 1, 2e-2, 20000)])
+def test_incremental_traversal_gives_the_same_lists(n, order, m2l_first, dt, rec_limit, monkeypatch):
     """Between rebuilds the traversal is updated from the previous one (re-classify every recorded pair, retire the
     subtrees of the pairs whose MAC flipped, re-expand those): after every step the lists must be the same SETS as a
     traversal from the root, and equal to the oracle's.  Large dt: many flips per step."""
     import torch
+    if rec_limit is not None:
+        monkeypatch.setenv("NBCO_REC_LIMIT", str(rec_limit))
     st = nb.init_ga(n)
     par = nb.default_param(n)
     dpar = torch.from_numpy(par).cuda()
