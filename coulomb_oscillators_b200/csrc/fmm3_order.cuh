@@ -823,8 +823,8 @@ struct OrderImpl
 	static bool fused_leaf_level(int64_t n, int L)
 	{
 		if (pad4<trl_off(P + 1)>() != 16 || L < 1 || (n & ((1ll << L) - 1)) != 0 || getenv("NBCO_NO_LEAF_FUSION")) return false; // the variable: A/B runs
-		const int64_t C = n >> L;
-		return C == 8 || C == 16 || C == 32;
+		return (n >> L) == 8; // the leaf size of the reference's level rule at order 3 and power-of-two N (s = order^2); 16 and 32
+		                      // particles per leaf (only reachable through max_level / dens_inhom at these orders) keep the two-kernel form
 	}
 	static int sparse_near(int64_t n, int L) { return fused_leaf_level(n, L) ? 1 : 0; } // l2lp_uniform_kernel honours t.nearbits
 	// nbco_fmm_get_tree: push the leaf level the fused kernel kept in registers (once per evaluation, fmm3.cu keeps the flag)
@@ -886,9 +886,7 @@ struct OrderImpl
 				const int leaf_lo = (int)(j_lo / C), leaf_hi = (int)(j_hi / C);
 				const int gridf = grid_for(4ll * (leaf_hi - leaf_lo), 128, ctx->sm_count, 16);
 #define NBCO_L2LP_UNIFORM(CC) l2lp_uniform_kernel<P, CC><<<gridf, 128, 0, st>>>(t, spos, acc_near, acc_out, perm_or_null, param, fuse_elastic, L, leaf_lo, leaf_hi, eps2, coll)
-				if (C == 8) NBCO_L2LP_UNIFORM(8);
-				else if (C == 16) NBCO_L2LP_UNIFORM(16);
-				else NBCO_L2LP_UNIFORM(32);
+				NBCO_L2LP_UNIFORM(8);
 #undef NBCO_L2LP_UNIFORM
 			}
 			++ctx->launches;
