@@ -114,3 +114,38 @@ def test_energy_of_two_particles():
     par = np.array([0.25, 0, 0, 2.0, 1.0, 1.0], np.float32)
     e = Oracle().energy(buf, n, par)
     assert np.allclose(e, [1.0, 0.5, 0.25], rtol=1e-6)
+
+
+def _chain_push(axis, chain):
+    """axes in order of most recent use, without repeats (fmm3_common.cuh: chain_push)"""
+    return [axis] + [a for a in chain if a != axis][:2]
+
+
+@pytest.mark.parametrize("n,max_level,quantise", [(3000, 2, False), (5000, 4, True), (4097, 3, True)])
+def test_order_inside_a_leaf_pair_is_the_total_order_of_their_parent(n, max_level, quantise):
+    """What the CUDA kd build relies on (kdtree.cu header): only the LAST level's order is observable, and it is the total order
+    (coordinate on the parent's split axis, coordinates on the previously used distinct axes, most recent first, input index) of
+    each level-(L-1) node.  That is also why a shallow tree can be finished with virtual levels that inherit the parent's axis
+    and chain.  Checked on the oracle's output, with many equal keys in the quantised cases."""
+    rng = np.random.default_rng(n)
+    pos = rng.normal(size=(n, 3)).astype(np.float32)
+    if quantise:
+        pos = (np.round(pos * 8) / 8).astype(np.float32)          # ~50 distinct values per axis
+    orc = Oracle(order=2, unsort=0, m2l_first=1, max_level=max_level)
+    sp = pos.copy()
+    orc.fmm3_kd(sp, None, nb.default_param(n))
+    T = orc.tree()
+    L = int(T["levels"])
+    assert L == max_level
+    perm, split, index, mult = T["perm"], T["splitdim"], T["index"], T["mult"]
+    assert np.array_equal(sp, pos[perm])
+    bits = pos.view(np.uint32)                                    # the sort key: fp32 bits made monotone (-0.0 sorts before +0.0)
+    ob = np.where(bits >> 31 == 0, bits ^ np.uint32(0x80000000), ~bits)
+    chains = {0: _chain_push(int(split[0]), [])}
+    for node in range(1, (1 << L) - 1):                           # nodes above the leaves
+        chains[node] = _chain_push(int(split[node]), chains[(node - 1) >> 1])
+    for node in range((1 << (L - 1)) - 1, (1 << L) - 1):          # level L-1
+        lo, cnt = int(index[node]), int(mult[node])
+        ids = perm[lo:lo + cnt]
+        keys = [tuple(int(ob[i, a]) for a in chains[node]) + (int(i),) for i in ids]
+        assert keys == sorted(keys), node
